@@ -1,0 +1,61 @@
+"""The UNet / loss restatements against fixtures produced by the reference's own model.py / loss.py
+(oracle/make_golden.py).  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiodenoiser_b200.checkpoint import seeded_state_dict, state_dict_spec, check_state_dict
+from oracle import unet_oracle, loss_oracle
+
+
+@pytest.fixture(scope="module")
+def sd7():
+    return seeded_state_dict(7)
+
+
+def test_state_dict_contract(sd7):
+    spec = state_dict_spec()
+    assert len(spec) == 136 and list(spec) == list(sd7)
+    n_params = sum(int(np.prod(s)) for k, (s, d) in spec.items() if d == torch.float32 and "running" not in k)
+    assert n_params == 31_042_369
+    assert sd7["downconv1.conv.double_conv.1.num_batches_tracked"].dtype == torch.int64
+    check_state_dict(sd7)
+    bad = dict(sd7); bad.pop("out.bias")
+    with pytest.raises(RuntimeError):
+        check_state_dict(bad)
+
+
+@pytest.mark.parametrize("name", ["small", "train", "test"])
+def test_unet_oracle_matches_reference_fixture(golden_dir, sd7, name):
+    z = np.load(os.path.join(golden_dir, f"unet_{name}.npz"))
+    y = unet_oracle.unet_forward(sd7, torch.from_numpy(z["x"])).numpy()
+    assert y.shape == z["y"].shape
+    assert np.max(np.abs(y - z["y"])) <= 2e-5 * np.max(np.abs(z["y"]))
+
+
+def test_unet_shapes_and_pad_side(sd7):
+    x = torch.rand(1, 1, 257, 188)
+    _, inter = unet_oracle.unet_forward(sd7, x, return_intermediates=True)
+    shapes = {k: tuple(v.shape[1:]) for k, v in inter.items()}
+    assert shapes == {"down1": (64, 257, 188), "down2": (128, 128, 94), "down3": (256, 64, 47), "down4": (512, 32, 23),
+                      "bottle": (1024, 16, 11), "up1": (512, 32, 23), "up2": (256, 64, 47), "up3": (128, 128, 94),
+                      "up4": (64, 257, 188)}
+
+
+@pytest.mark.parametrize("name", ["train", "test"])
+def test_loss_oracle_matches_reference_fixture(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"loss_{name}.npz"))
+    p = torch.from_numpy(z["pred"].astype(np.float32)); t = torch.from_numpy(z["target"].astype(np.float32))
+    vals = [float(v) for v in loss_oracle.combined_loss(p, t)]
+    assert np.allclose(vals, z["values"], rtol=2e-5, atol=1e-7)
+
+
+def test_loss_seed0_regression(golden_dir):
+    torch.manual_seed(0)
+    p, t = torch.rand(4, 1, 256, 64), torch.rand(4, 1, 256, 64)
+    vals = [float(v) for v in loss_oracle.combined_loss(p, t)]
+    ref = np.load(os.path.join(golden_dir, "loss_seed0.npz"))["values"]
+    assert np.allclose(vals, ref, rtol=2e-5)
+    assert np.allclose(ref, [0.0999247, 0.0634807, 0.0203401, 0.3319817], rtol=1e-5)   # SURVEY Appendix A probe
