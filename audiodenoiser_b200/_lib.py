@@ -1,0 +1,108 @@
+"""ctypes binding of libadn_b200.so (C ABI in include/adn_b200.h).
+
+There is no CPU fallback: if the library cannot be loaded, or the current device is not a B200-class GPU,
+every call raises.  The library is built in-tree by ``python -m audiodenoiser_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p, c_char_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libadn_b200.so")
+
+_lock = threading.Lock()
+_lib = None
+
+P = c_void_p
+
+# name -> (restype, argtypes); mirrors include/adn_b200.h one to one
+SIGNATURES = {
+    "adn_version": (c_int, []),
+    "adn_error_string": (c_char_p, [c_int]),
+    "adn_last_cuda_error": (c_int, []),
+    "adn_device_check": (c_int, []),
+    "adn_stft_num_frames": (c_int64, [c_int64, c_int]),
+    "adn_stft_mag_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
+    "adn_stft_complex_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
+    "adn_istft_ola_f32": (c_int, [P, P, c_int, c_uint64, c_int64, c_int64, P, P]),
+    "adn_stft_mag_host_f32": (c_int, [P, c_int64, c_int64, c_int, P]),
+    "adn_istft_ola_host_f32": (c_int, [P, P, c_uint64, c_int64, c_int64, P]),
+    "adn_pack_conv3x3_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
+    "adn_pack_convt2x2_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
+    "adn_fold_bn_f32": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P]),
+    "adn_conv3x3_c1_bn_relu_bf16": (c_int, [P, c_int, c_int, c_int, P, P, P, P, P]),
+    "adn_conv3x3_bn_relu_bf16": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, P]),
+    "adn_conv3x3_bn_relu_head_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P, P, P, P]),
+    "adn_convt2x2_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "adn_maxpool2x2_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "adn_nhwc_bf16_to_nchw_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "adn_nchw_f32_to_nhwc_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
+    "adn_spec_f16_crop_f32": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
+    "adn_spec_error_sums_f64": (c_int, [P, P, c_int64, P, P]),
+}
+
+
+class AdnError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Load (once) and return the ctypes handle.  Raises AdnError when the native library is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH) and build_if_missing:
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as exc:  # noqa: BLE001
+                raise AdnError(f"libadn_b200.so is missing and could not be built: {exc}") from exc
+        if not os.path.exists(LIB_PATH):
+            raise AdnError(f"{LIB_PATH} not found: run `python -m audiodenoiser_b200.build` (no CPU fallback exists)")
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as exc:
+            raise AdnError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:
+                raise AdnError(f"{LIB_PATH} does not export {name}; rebuild it") from exc
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    """Translate an adn_status into a Python exception (ValueError for argument errors, AdnError otherwise)."""
+    if status == 0:
+        return
+    lib = load()
+    msg = lib.adn_error_string(status).decode()
+    if status == 2:
+        msg += f" [cudaError {lib.adn_last_cuda_error()}]"
+    text = f"{what}: {msg}" if what else msg
+    if status in (1, 5):
+        raise ValueError(text)
+    raise AdnError(text)
+
+
+def require_cuda():
+    """The product path needs a CUDA device; say so plainly instead of falling back."""
+    import torch
+    if not torch.cuda.is_available():
+        raise AdnError("audiodenoiser_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def stream_ptr(torch_stream=None) -> int:
+    import torch
+    s = torch_stream if torch_stream is not None else torch.cuda.current_stream()
+    return int(s.cuda_stream)

@@ -1,0 +1,97 @@
+// Shared helpers for libadn_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/adn_b200.h"
+
+namespace adn {
+
+void set_last_cuda_error(cudaError_t e);   // abi.cu (thread-local)
+int check_device();                        // abi.cu: ADN_OK iff current device is sm_100
+
+#define ADN_CUDA_TRY(expr)                                  \
+    do {                                                    \
+        cudaError_t _e = (expr);                            \
+        if (_e != cudaSuccess) {                            \
+            ::adn::set_last_cuda_error(_e);                 \
+            return ADN_ERR_CUDA;                            \
+        }                                                   \
+    } while (0)
+
+#define ADN_LAUNCH_CHECK() ADN_CUDA_TRY(cudaGetLastError())
+
+inline int num_sms() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+// ---------------------------------------------------------------- small complex helpers (float2 = re, im)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {   // a * conj(b)
+    return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+
+// 4-point DFT, in place.  INV = false: forward (W4 = -i); INV = true: inverse (W4 = +i), unnormalised.
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    float2 a0 = cadd(x0, x2), a1 = csub(x0, x2), a2 = cadd(x1, x3), a3 = csub(x1, x3);
+    x0 = cadd(a0, a2);
+    x2 = csub(a0, a2);
+    // forward: x1 = a1 - i*a3, x3 = a1 + i*a3 ; (-i)*(re,im) = (im,-re)
+    float2 r = INV ? make_float2(-a3.y, a3.x) : make_float2(a3.y, -a3.x);
+    x1 = cadd(a1, r);
+    x3 = csub(a1, r);
+}
+
+// multiply by W16^M (forward, exp(-2 pi i M/16)) or its conjugate (INV)
+template <int M, bool INV>
+__device__ __forceinline__ float2 tw16(float2 v) {
+    constexpr float C8 = 0.70710678118654752440f;   // cos(pi/4)
+    constexpr float C1 = 0.92387953251128675613f;   // cos(pi/8)
+    constexpr float S1 = 0.38268343236508977173f;   // sin(pi/8)
+    if constexpr (M == 0) return v;
+    else if constexpr (M == 4) return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+    else if constexpr (M == 2) return INV ? make_float2((v.x - v.y) * C8, (v.x + v.y) * C8)
+                                           : make_float2((v.x + v.y) * C8, (v.y - v.x) * C8);
+    else if constexpr (M == 6) return INV ? make_float2(-(v.x + v.y) * C8, (v.x - v.y) * C8)
+                                           : make_float2((v.y - v.x) * C8, -(v.x + v.y) * C8);
+    else {
+        // general: w = (cos a, -sin a) forward with a = 2 pi M / 16
+        constexpr float wr = (M == 1) ? C1 : (M == 3) ? S1 : /*M == 9*/ -C1;
+        constexpr float wi_f = (M == 1) ? -S1 : (M == 3) ? -C1 : /*M == 9*/ S1;
+        const float wi = INV ? -wi_f : wi_f;
+        return make_float2(fmaf(v.x, wr, -v.y * wi), fmaf(v.x, wi, v.y * wr));
+    }
+}
+
+// 16-point DFT in registers, natural order in and out (v[k] <- sum_n v[n] W16^{nk}).
+template <bool INV>
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // n = 4*n1 + n2 ; k = k1 + 4*k2.  Stage A: DFT over n1 for each n2.
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+    // now v[4*k1 + n2] holds y[k1][n2]; twiddle by W16^{n2*k1}
+    v[5] = tw16<1, INV>(v[5]);   v[6] = tw16<2, INV>(v[6]);   v[7] = tw16<3, INV>(v[7]);
+    v[9] = tw16<2, INV>(v[9]);   v[10] = tw16<4, INV>(v[10]); v[11] = tw16<6, INV>(v[11]);
+    v[13] = tw16<3, INV>(v[13]); v[14] = tw16<6, INV>(v[14]); v[15] = tw16<9, INV>(v[15]);
+    // Stage B: DFT over n2 for each k1: results X[k1 + 4*k2] land in v[4*k1 + k2]
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) dft4<INV>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    // transpose 4x4 so that v[k1 + 4*k2] = X[k1 + 4*k2]
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = a + 1; b < 4; ++b) {
+            float2 t = v[4 * a + b];
+            v[4 * a + b] = v[4 * b + a];
+            v[4 * b + a] = t;
+        }
+}
+
+}  // namespace adn

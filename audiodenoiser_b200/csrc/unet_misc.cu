@@ -1,0 +1,272 @@
+// unet_misc.cu -- the HBM-bound pieces around the tcgen05 convolutions of the reference UNet (code/model.py):
+// checkpoint packing, BN folding, the Cin=1 first layer (direct conv), 2x2 max-pool, layout converters, the
+// SpectrogramDataset transform (code/data_loader.py:41-72) and error statistics.
+#include "adn_common.cuh"
+
+namespace adn {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, int co_n, int ci_n, __nv_bfloat16* __restrict__ out) {
+    const long long total = (long long)co_n * 9 * ci_n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % ci_n);
+        const int tap = (int)((i / ci_n) % 9);
+        const int co = (int)(i / ((long long)ci_n * 9));
+        out[i] = __float2bfloat16_rn(w[((long long)co * ci_n + ci) * 9 + tap]);
+    }
+}
+
+__global__ void pack_convt2x2_kernel(const float* __restrict__ w, int ci_n, int co_n, __nv_bfloat16* __restrict__ out) {
+    const long long total = 4ll * co_n * ci_n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % ci_n);
+        const int co = (int)((i / ci_n) % co_n);
+        const int q = (int)(i / ((long long)ci_n * co_n));
+        out[i] = __float2bfloat16_rn(w[((long long)ci * co_n + co) * 4 + q]);
+    }
+}
+
+__global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = fmaf((conv_bias ? conv_bias[i] : 0.f) - mean[i], s, beta[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ first layer
+// (n,1,h,w) fp32 -> conv3x3 pad 1 (64 filters, fp32 math) -> folded BN -> ReLU -> NHWC bf16.
+// 8 lanes per pixel, 8 output channels per lane: each lane stores 16 B, a warp stores 4 pixels x 128 B contiguously.
+__global__ void __launch_bounds__(256)
+conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float* __restrict__ weight,
+                  const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ out) {
+    __shared__ __align__(16) float s_w[9][64];
+    __shared__ float s_scale[64], s_shift[64];
+    for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w[i % 9][i / 9] = weight[i];   // weight[c][tap]
+    if (threadIdx.x < 64) { s_scale[threadIdx.x] = scale[threadIdx.x]; s_shift[threadIdx.x] = shift[threadIdx.x]; }
+    __syncthreads();
+    const long long total = (long long)n * h * w * 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i & 7);
+        const long long pix = i >> 3;
+        const int px = (int)(pix % w);
+        const int py = (int)((pix / w) % h);
+        const long long img = pix / ((long long)w * h);
+        const float* __restrict__ xi = x + img * (long long)h * w;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int xx = px + kx - 1;
+                const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + (long long)yy * w + xx) : 0.f;
+                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8 + 4]);
+                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+            }
+        }
+        float y[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[c], s_scale[cg * 8 + c], s_shift[cg * 8 + c]), 0.f);
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+        out[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ max-pool
+__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bmax8(uint4 a, uint4 b) {
+    return make_uint4(bmax2(a.x, b.x), bmax2(a.y, b.y), bmax2(a.z, b.z), bmax2(a.w, b.w));
+}
+
+__global__ void __launch_bounds__(256)
+maxpool2x2_kernel(const uint4* __restrict__ src, int n, int h, int w, int c8, uint4* __restrict__ dst) {
+    const int ho = h >> 1, wo = w >> 1;
+    const long long total = (long long)n * ho * wo * c8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c8);
+        const int xo = (int)((i / c8) % wo);
+        const int yo = (int)((i / ((long long)c8 * wo)) % ho);
+        const long long img = i / ((long long)c8 * wo * ho);
+        const long long r0 = ((img * h + 2 * yo) * w + 2 * xo) * c8 + c;
+        const long long r1 = r0 + (long long)w * c8;
+        const uint4 a = __ldg(src + r0), b = __ldg(src + r0 + c8), cc = __ldg(src + r1), d = __ldg(src + r1 + c8);
+        dst[i] = bmax8(bmax8(a, b), bmax8(cc, d));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ layout converters
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ src, int n, int h, int w, int c, float* __restrict__ dst) {
+    const long long total = (long long)n * h * w * c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % w);
+        const int yy = (int)((i / w) % h);
+        const int cc = (int)((i / ((long long)w * h)) % c);
+        const long long img = i / ((long long)w * h * c);
+        dst[i] = __bfloat162float(src[((img * h + yy) * w + xx) * c + cc]);
+    }
+}
+
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ src, int n, int c, int h, int w, __nv_bfloat16* __restrict__ dst) {
+    const long long total = (long long)n * h * w * c;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cc = (int)(i % c);
+        const int xx = (int)((i / c) % w);
+        const int yy = (int)((i / ((long long)c * w)) % h);
+        const long long img = i / ((long long)c * w * h);
+        dst[i] = __float2bfloat16_rn(src[((img * c + cc) * h + yy) * w + xx]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ loader transform
+__global__ void spec_f16_crop_kernel(const float* __restrict__ src, long long n, int f_in, int t_in, int f_out, int t_out,
+                                     float* __restrict__ dst) {
+    const long long total = n * f_out * t_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % t_out);
+        const int f = (int)((i / t_out) % f_out);
+        const long long img = i / ((long long)t_out * f_out);
+        float v = 0.f;
+        if (f < f_in && t < t_in) v = __half2float(__float2half_rn(src[(img * f_in + f) * t_in + t]));
+        dst[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ error statistics
+__global__ void __launch_bounds__(256)
+spec_error_sums_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long count, double* __restrict__ sums) {
+    double s_abs = 0.0, s_sig = 0.0, s_err = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const float p = pred[i], t = target[i];
+        const float d = t - p;
+        s_abs += (double)fabsf(d);
+        s_sig += (double)t * (double)t;
+        s_err += (double)d * (double)d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s_abs += __shfl_xor_sync(0xffffffffu, s_abs, o);
+        s_sig += __shfl_xor_sync(0xffffffffu, s_sig, o);
+        s_err += __shfl_xor_sync(0xffffffffu, s_err, o);
+    }
+    __shared__ double sh[3][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = s_abs; sh[1][warp] = s_sig; sh[2][warp] = s_err; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sh[threadIdx.x][k];
+        atomicAdd(&sums[threadIdx.x], t);
+    }
+}
+
+static inline int grid_for(long long total, int block = 256) {
+    long long g = (total + block - 1) / block;
+    const long long cap = (long long)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" int adn_pack_conv3x3_weight_bf16(const float* w, int c_out, int c_in, void* packed, void* stream) {
+    if (!w || !packed || c_out <= 0 || c_in <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    const long long total = (long long)c_out * 9 * c_in;
+    pack_conv3x3_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, c_out, c_in, (__nv_bfloat16*)packed);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_pack_convt2x2_weight_bf16(const float* w, int c_in, int c_out, void* packed, void* stream) {
+    if (!w || !packed || c_out <= 0 || c_in <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    const long long total = 4ll * c_out * c_in;
+    pack_convt2x2_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, c_in, c_out, (__nv_bfloat16*)packed);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_fold_bn_f32(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,
+                               float eps, int channels, float* scale, float* shift, void* stream) {
+    if (!gamma || !beta || !mean || !var || !scale || !shift || channels <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    fold_bn_kernel<<<(channels + 127) / 128, 128, 0, (cudaStream_t)stream>>>(conv_bias, gamma, beta, mean, var, eps, channels, scale, shift);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_conv3x3_c1_bn_relu_bf16(const float* x, int n, int h, int w, const float* weight, const float* scale,
+                                           const float* shift, void* out, void* stream) {
+    if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, (uint4*)out);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_maxpool2x2_bf16(const void* src, int n, int h, int w, int c, void* out, void* stream) {
+    if (!src || !out || n <= 0 || h < 2 || w < 2 || c <= 0 || (c & 7)) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    maxpool2x2_kernel<<<grid_for((long long)n * (h / 2) * (w / 2) * (c / 8)), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)src, n, h, w, c / 8, (uint4*)out);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_nhwc_bf16_to_nchw_f32(const void* src, int n, int h, int w, int c, float* dst, void* stream) {
+    if (!src || !dst || n <= 0 || h <= 0 || w <= 0 || c <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    nhwc_bf16_to_nchw_f32_kernel<<<grid_for((long long)n * h * w * c), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, n, h, w, c, dst);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_nchw_f32_to_nhwc_bf16(const float* src, int n, int c, int h, int w, void* dst, void* stream) {
+    if (!src || !dst || n <= 0 || h <= 0 || w <= 0 || c <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    nchw_f32_to_nhwc_bf16_kernel<<<grid_for((long long)n * h * w * c), 256, 0, (cudaStream_t)stream>>>(src, n, c, h, w, (__nv_bfloat16*)dst);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_spec_f16_crop_f32(const float* src, int64_t n, int f_in, int t_in, int f_out, int t_out, float* dst, void* stream) {
+    if (n < 0 || f_in <= 0 || t_in <= 0 || f_out <= 0 || t_out <= 0) return ADN_ERR_ARG;
+    if (n == 0) return ADN_OK;
+    if (!src || !dst) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    spec_f16_crop_kernel<<<grid_for((long long)n * f_out * t_out), 256, 0, (cudaStream_t)stream>>>(src, n, f_in, t_in, f_out, t_out, dst);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_spec_error_sums_f64(const float* pred, const float* target, int64_t count, double* sums, void* stream) {
+    if (count < 0 || !sums) return ADN_ERR_ARG;
+    if (count == 0) return ADN_OK;
+    if (!pred || !target) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    spec_error_sums_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(pred, target, count, sums);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}

@@ -1,0 +1,202 @@
+"""Drop-in for the reference's code/model.py ``UNet`` -- same constructor, same 136-entry ``state_dict`` (so existing
+``unet_denoiser_{noise}.pth`` checkpoints load, test.py:63-66), same ``forward(x)`` contract ((N,1,F,T) float32 in,
+(N,1,F,T) float32 out on the input's device) -- whose forward runs the hand-written sm_100a kernels of
+libadn_b200.so: bf16 operands, fp32 accumulation in TMEM, fp32 BatchNorm/ReLU epilogues.
+
+The module holds fp32 master parameters in the reference layout; a packed copy (bf16 K-major weights, folded BN
+scale/shift) is rebuilt whenever they change.  Only the eval-mode (running-statistics) forward exists in this round;
+``forward`` in training mode raises.  No CPU path: non-CUDA input raises.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .checkpoint import BN_EPS, state_dict_spec
+
+_MAX_CHUNK = 64          # images per kernel batch (bounds the activation workspace; test.py:113 feeds the whole set)
+
+
+class _Holder(nn.Module):
+    """Attribute container: lets parameters sit under the reference's dotted names."""
+
+
+def _attach(root: nn.Module, dotted: str, tensor: torch.Tensor, is_buffer: bool) -> None:
+    parts = dotted.split(".")
+    mod = root
+    for p in parts[:-1]:
+        if not hasattr(mod, p):
+            mod.add_module(p, _Holder())
+        mod = getattr(mod, p)
+    if is_buffer:
+        mod.register_buffer(parts[-1], tensor)
+    else:
+        mod.register_parameter(parts[-1], nn.Parameter(tensor))
+
+
+class UNet(nn.Module):
+    """model.py:53-94.  ``UNet(in_channels=1, num_classes=1)``."""
+
+    def __init__(self, in_channels=1, num_classes=1):
+        super().__init__()
+        if in_channels != 1 or num_classes != 1:
+            raise ValueError("the B200 build is specialised to the reference's UNet(in_channels=1, num_classes=1)")
+        g = torch.Generator().manual_seed(0)
+        for key, (shape, dtype) in state_dict_spec().items():
+            leaf = key.rsplit(".", 1)[1]
+            is_buffer = leaf in ("running_mean", "running_var", "num_batches_tracked")
+            is_bn = ".double_conv.1." in key or ".double_conv.4." in key
+            if dtype == torch.int64:
+                t = torch.zeros((), dtype=torch.int64)
+            elif is_bn:
+                t = torch.ones(shape) if leaf in ("weight", "running_var") else torch.zeros(shape)
+            elif len(shape) == 4:
+                fan_in = shape[1] * shape[2] * shape[3]
+                bound = (1.0 / fan_in) ** 0.5                      # same scale as nn.Conv2d's default init
+                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
+            else:
+                t = torch.zeros(shape)                             # conv / conv-transpose / head bias
+            _attach(self, key, t, is_buffer)
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+
+    # ------------------------------------------------------------------ packing
+    def _version_key(self, device):
+        return (str(device),) + tuple(int(v._version) for v in self.state_dict(keep_vars=True).values())
+
+    def _pack(self, device):
+        """fp32 reference-layout tensors -> bf16 [Co][tap][Ci] weights + folded fp32 BN scale/shift, on `device`."""
+        lib = _lib.load()
+        s = _lib.stream_ptr()
+        sd = {k: v.detach().to(device=device) for k, v in self.state_dict(keep_vars=True).items()}
+        packed = {}
+
+        def conv(prefix, idx_conv, idx_bn, first=False):
+            w = sd[f"{prefix}.double_conv.{idx_conv}.weight"].float().contiguous()
+            co, ci = w.shape[0], w.shape[1]
+            scale = torch.empty(co, dtype=torch.float32, device=device)
+            shift = torch.empty(co, dtype=torch.float32, device=device)
+            bn = f"{prefix}.double_conv.{idx_bn}"
+            args = [sd[f"{prefix}.double_conv.{idx_conv}.bias"], sd[f"{bn}.weight"], sd[f"{bn}.bias"], sd[f"{bn}.running_mean"],
+                    sd[f"{bn}.running_var"]]
+            args = [a.float().contiguous() for a in args]
+            _lib.check(lib.adn_fold_bn_f32(*[a.data_ptr() for a in args], BN_EPS, co, scale.data_ptr(), shift.data_ptr(), s), "adn_fold_bn_f32")
+            if first:
+                return {"w": w, "scale": scale, "shift": shift, "co": co, "ci": ci, "keep": args}
+            wp = torch.empty((co, 9, ci), dtype=torch.bfloat16, device=device)
+            _lib.check(lib.adn_pack_conv3x3_weight_bf16(w.data_ptr(), co, ci, wp.data_ptr(), s), "adn_pack_conv3x3_weight_bf16")
+            return {"w": wp, "scale": scale, "shift": shift, "co": co, "ci": ci, "keep": (w, args)}
+
+        for name in ("downconv1", "downconv2", "downconv3", "downconv4"):
+            packed[f"{name}.0"] = conv(f"{name}.conv", 0, 1, first=(name == "downconv1"))
+            packed[f"{name}.3"] = conv(f"{name}.conv", 3, 4)
+        packed["bottleneck.0"] = conv("bottleneck", 0, 1)
+        packed["bottleneck.3"] = conv("bottleneck", 3, 4)
+        for name in ("upconv1", "upconv2", "upconv3", "upconv4"):
+            w = sd[f"{name}.up.weight"].float().contiguous()
+            ci, co = w.shape[0], w.shape[1]
+            wp = torch.empty((4, co, ci), dtype=torch.bfloat16, device=device)
+            _lib.check(lib.adn_pack_convt2x2_weight_bf16(w.data_ptr(), ci, co, wp.data_ptr(), s), "adn_pack_convt2x2_weight_bf16")
+            packed[f"{name}.up"] = {"w": wp, "bias": sd[f"{name}.up.bias"].float().contiguous(), "co": co, "ci": ci, "keep": w}
+            packed[f"{name}.0"] = conv(f"{name}.conv", 0, 1)
+            packed[f"{name}.3"] = conv(f"{name}.conv", 3, 4)
+        packed["out"] = {"w": sd["out.weight"].float().reshape(-1).contiguous(), "b": sd["out.bias"].float().contiguous()}
+        return packed
+
+    def packed(self, device):
+        key = self._version_key(device)
+        if self._packed is None or self._packed_key != key:
+            with torch.cuda.device(device):
+                self._packed = self._pack(device)
+            self._packed_key = key
+            self._ws = {}
+        return self._packed
+
+    # ------------------------------------------------------------------ forward
+    def _workspace(self, n, h, w, device):
+        key = (n, h, w, str(device))
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        bf = dict(dtype=torch.bfloat16, device=device)
+        hs, wsz = [h], [w]
+        for _ in range(4):
+            hs.append(hs[-1] // 2)
+            wsz.append(wsz[-1] // 2)
+        if hs[4] < 1 or wsz[4] < 1:
+            raise ValueError(f"input {h}x{w} is too small for four 2x2 poolings")
+        ch = [64, 128, 256, 512, 1024]
+        ws = {"hs": hs, "ws": wsz}
+        for l in range(5):
+            ws[f"a{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)      # first conv of the level
+            ws[f"s{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)      # second conv = skip / bottleneck out
+            if l < 4:
+                ws[f"p{l}"] = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), **bf)          # pooled
+                ws[f"u{l}"] = torch.empty((n, 2 * hs[l + 1], 2 * wsz[l + 1], ch[l]), **bf)  # up-sampled into level l
+                ws[f"ua{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
+                ws[f"ub{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
+        self._ws = {key: ws}          # keep one shape resident
+        return ws
+
+    def _forward_chunk(self, x, out, pk):
+        lib = _lib.load()
+        s = _lib.stream_ptr()
+        n, _, h, w = x.shape
+        ws = self._workspace(n, h, w, x.device)
+        hs, wz = ws["hs"], ws["ws"]
+
+        def conv(layer, src0, c0, src1, c1, h1, w1, lvl, dst, pool=None):
+            p = pk[layer]
+            st = lib.adn_conv3x3_bn_relu_bf16(src0.data_ptr(), c0, src1.data_ptr() if src1 is not None else 0, c1, h1, w1,
+                                              n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"], p["scale"].data_ptr(),
+                                              p["shift"].data_ptr(), dst.data_ptr(), pool.data_ptr() if pool is not None else 0, s)
+            _lib.check(st, f"adn_conv3x3_bn_relu_bf16[{layer}]")
+
+        # encoder (DownSampleLayer.forward, model.py:29-32)
+        p = pk["downconv1.0"]
+        _lib.check(lib.adn_conv3x3_c1_bn_relu_bf16(x.data_ptr(), n, h, w, p["w"].data_ptr(), p["scale"].data_ptr(),
+                                                   p["shift"].data_ptr(), ws["a0"].data_ptr(), s), "adn_conv3x3_c1_bn_relu_bf16")
+        conv("downconv1.3", ws["a0"], 64, None, 0, 0, 0, 0, ws["s0"], ws["p0"])
+        ch = [64, 128, 256, 512, 1024]
+        for l in (1, 2, 3):
+            conv(f"downconv{l + 1}.0", ws[f"p{l - 1}"], ch[l - 1], None, 0, 0, 0, l, ws[f"a{l}"])
+            conv(f"downconv{l + 1}.3", ws[f"a{l}"], ch[l], None, 0, 0, 0, l, ws[f"s{l}"], ws[f"p{l}"])
+        conv("bottleneck.0", ws["p3"], 512, None, 0, 0, 0, 4, ws["a4"])
+        conv("bottleneck.3", ws["a4"], 1024, None, 0, 0, 0, 4, ws["s4"])
+        # decoder (UpSampleLayer.forward, model.py:41-50)
+        cur = ws["s4"]
+        for i, l in enumerate((3, 2, 1, 0)):
+            name = f"upconv{i + 1}"
+            pu = pk[f"{name}.up"]
+            st = lib.adn_convt2x2_bf16(cur.data_ptr(), pu["ci"], n, hs[l + 1], wz[l + 1], pu["w"].data_ptr(), pu["co"],
+                                       pu["bias"].data_ptr(), ws[f"u{l}"].data_ptr(), s)
+            _lib.check(st, f"adn_convt2x2_bf16[{name}]")
+            conv(f"{name}.0", ws[f"s{l}"], ch[l], ws[f"u{l}"], ch[l], 2 * hs[l + 1], 2 * wz[l + 1], l, ws[f"ua{l}"])
+            if l > 0:
+                conv(f"{name}.3", ws[f"ua{l}"], ch[l], None, 0, 0, 0, l, ws[f"ub{l}"])
+                cur = ws[f"ub{l}"]
+            else:
+                p = pk[f"{name}.3"]
+                st = lib.adn_conv3x3_bn_relu_head_f32(ws["ua0"].data_ptr(), 64, 0, 0, 0, 0, n, h, w, p["w"].data_ptr(), 64,
+                                                      p["scale"].data_ptr(), p["shift"].data_ptr(), pk["out"]["w"].data_ptr(),
+                                                      pk["out"]["b"].data_ptr(), out.data_ptr(), s)
+                _lib.check(st, "adn_conv3x3_bn_relu_head_f32")
+
+    def forward(self, x):
+        """UNet.forward, model.py:70-94 (eval-mode BatchNorm)."""
+        _lib.require_cuda()
+        if self.training:
+            raise NotImplementedError("audiodenoiser_b200.UNet: only the eval()-mode forward is implemented on the B200 path")
+        if not x.is_cuda:
+            raise _lib.AdnError("UNet.forward needs a CUDA tensor (no CPU fallback); move the input with .cuda()")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError("expected (N, 1, F, T) input")
+        x = x.float().contiguous()
+        with torch.cuda.device(x.device), torch.no_grad():
+            pk = self.packed(x.device)
+            out = torch.empty_like(x)
+            for i in range(0, x.shape[0], _MAX_CHUNK):
+                self._forward_chunk(x[i:i + _MAX_CHUNK], out[i:i + _MAX_CHUNK], pk)
+        return out

@@ -1,0 +1,109 @@
+"""Batched device-resident spectral front / back end (SURVEY 8b "batched fast path").
+
+``stft_mag_batched`` / ``istft_batched`` take and return CUDA tensors and launch the sm_100a kernels of
+libadn_b200.so on the current torch stream.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+from . import _lib
+
+N_FFT = 512
+HOP_LENGTH = 128
+N_BINS = N_FFT // 2 + 1
+
+
+def num_frames(length: int, center: bool) -> int:
+    """1 + (L [+ 512] - 512)//128 -- librosa.stft's frame count; raises like librosa when too short."""
+    t = _lib.load().adn_stft_num_frames(int(length), int(bool(center)))
+    if t < 0:
+        raise ValueError(f"Input signal length={length} is too small to analyze with n_fft={N_FFT}")
+    return int(t)
+
+
+def _check_wave(wave):
+    torch = _lib.require_cuda()
+    if not isinstance(wave, torch.Tensor) or not wave.is_cuda:
+        raise _lib.AdnError("expected a CUDA tensor (no CPU fallback)")
+    if wave.dim() == 1:
+        wave = wave.unsqueeze(0)
+    if wave.dim() != 2:
+        raise ValueError("wave must be (L,) or (N, L)")
+    if wave.dtype != torch.float32:
+        wave = wave.float()
+    if wave.stride(1) != 1 or (wave.shape[0] > 1 and wave.stride(0) < wave.shape[1]):
+        wave = wave.contiguous()
+    return torch, wave
+
+
+def stft_mag_batched(wave, center: bool = True, out=None):
+    """(N, L) float32 CUDA -> (N, 257, T) float32 |STFT| (n_fft=512, hop=128, periodic Hann).
+    center=True zero-pads 256 samples each side (create_test_dataset.py:39); center=False is the
+    train-path framing (create_train_dataset.py:167-172)."""
+    torch, wave = _check_wave(wave)
+    n, length = wave.shape
+    t = num_frames(length, center)
+    if out is None:
+        out = torch.empty((n, N_BINS, t), dtype=torch.float32, device=wave.device)
+    elif tuple(out.shape) != (n, N_BINS, t) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 (N,257,T) tensor")
+    stride = wave.stride(0) if n > 1 else max(length, 1)
+    with torch.cuda.device(wave.device):
+        st = _lib.load().adn_stft_mag_f32(wave.data_ptr(), n, length, stride, int(bool(center)), out.data_ptr(), _lib.stream_ptr())
+    _lib.check(st, "adn_stft_mag_f32")
+    return out
+
+
+def stft_complex_batched(wave, center: bool = True):
+    """(N, L) float32 CUDA -> (N, 257, T) complex64 STFT (librosa.stft at test.py:41)."""
+    torch, wave = _check_wave(wave)
+    n, length = wave.shape
+    t = num_frames(length, center)
+    out = torch.empty((n, N_BINS, t), dtype=torch.complex64, device=wave.device)
+    stride = wave.stride(0) if n > 1 else max(length, 1)
+    with torch.cuda.device(wave.device):
+        st = _lib.load().adn_stft_complex_f32(wave.data_ptr(), n, length, stride, int(bool(center)), out.data_ptr(), _lib.stream_ptr())
+    _lib.check(st, "adn_stft_complex_f32")
+    return out
+
+
+def istft_batched(mag, phasor=None, seed: int = 0, out=None):
+    """Inverse STFT + overlap-add: (N,257,T) magnitude x (N,257,T) complex64 unit phasor -> (N, 128*(T-1)) float32.
+
+    ``phasor=None`` draws a uniform random phase on the device from ``seed`` (test.py:36 uses the unseeded numpy RNG).
+    A complex ``mag`` is taken as the complex spectrogram itself (librosa.istft at test.py:40)."""
+    torch = _lib.require_cuda()
+    if not isinstance(mag, torch.Tensor) or not mag.is_cuda:
+        raise _lib.AdnError("expected a CUDA tensor (no CPU fallback)")
+    if mag.dim() == 2:
+        mag = mag.unsqueeze(0)
+    if mag.dim() != 3 or mag.shape[1] != N_BINS:
+        raise ValueError("spectrogram must be (257, T) or (N, 257, T)")
+    n, _, t = mag.shape
+    is_complex = mag.is_complex()
+    if is_complex:
+        if phasor is not None:
+            raise ValueError("phasor must be None when the spectrogram is complex")
+        spec = mag.to(torch.complex64).contiguous()
+        mag_ptr, ph_ptr = 0, spec.data_ptr()
+    else:
+        mag = mag.float().contiguous()
+        mag_ptr = mag.data_ptr()
+        if phasor is not None:
+            if phasor.dim() == 2:
+                phasor = phasor.unsqueeze(0)
+            if tuple(phasor.shape) != tuple(mag.shape):
+                raise ValueError("phasor must have the magnitude's shape")
+            phasor = phasor.to(device=mag.device, dtype=torch.complex64).contiguous()
+            ph_ptr = phasor.data_ptr()
+        else:
+            ph_ptr = 0
+    n_out = HOP_LENGTH * (t - 1)
+    if out is None:
+        out = torch.empty((n, n_out), dtype=torch.float32, device=mag.device)
+    elif tuple(out.shape) != (n, n_out) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous float32 (N, 128*(T-1)) tensor")
+    with torch.cuda.device(mag.device):
+        st = _lib.load().adn_istft_ola_f32(mag_ptr, ph_ptr, int(is_complex), int(seed) & 0xFFFFFFFFFFFFFFFF, n, t,
+                                           out.data_ptr(), _lib.stream_ptr())
+    _lib.check(st, "adn_istft_ola_f32")
+    return out
