@@ -21,10 +21,31 @@ int check_device();                        // abi.cu: ADN_OK iff current device 
 
 #define ADN_LAUNCH_CHECK() ADN_CUDA_TRY(cudaGetLastError())
 
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
 inline int num_sms() {
-    int dev = 0, n = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    static int cache[64] = {0};
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (dev >= 0 && dev < 64) cache[dev] = n;
     return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): keeps launches free of non-stream calls so
+// they can be captured into CUDA graphs.  `flags` is a per-kernel static array of 64 bytes.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, unsigned char* flags) {
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64 && flags[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) flags[dev] = 1;
+    return e;
 }
 
 // ---------------------------------------------------------------- small complex helpers (float2 = re, im)

@@ -393,7 +393,8 @@ template <int BLOCK_N>
 static int launch_cfg(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const ConvArgs& args, cudaStream_t stream) {
     using Cfg = ConvCfg<BLOCK_N>;
     auto kern = conv_gemm_kernel<BLOCK_N>;
-    ADN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(kern, Cfg::SMEM_BYTES, smem_set));
     const int sms = num_sms();
     const int grid = args.num_tiles < sms ? args.num_tiles : sms;
     kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(mA0, mA1, mB, args);

@@ -178,7 +178,8 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
     const float2* ph = reinterpret_cast<const float2*>(phasor);
 #define ADN_ISTFT_LAUNCH(MODE)                                                                                     \
     do {                                                                                                           \
-        ADN_CUDA_TRY(cudaFuncSetAttribute(istft_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static unsigned char smem_set[64] = {0};                                                                   \
+        ADN_CUDA_TRY(ensure_dyn_smem(istft_kernel<MODE>, (int)smem, smem_set));                                    \
         istft_kernel<MODE><<<grid, IS_THREADS, smem, stream>>>(mag, ph, (unsigned long long)seed, n_clips, (int)n_frames, \
                                                                tiles_per_clip, audio);                             \
     } while (0)

@@ -177,7 +177,8 @@ static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64
     const long long total = (long long)n_clips * tiles_per_clip;
     const size_t smem = sizeof(StftSmem<COMPLEX_OUT>);
     auto kern = stft_kernel<COMPLEX_OUT>;
-    ADN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(kern, (int)smem, smem_set));
     const long long max_grid = (long long)num_sms() * 2 * 8;     // 2 resident CTAs per SM, 8 waves before looping
     const int grid = (int)(total < max_grid ? total : max_grid);
     kern<<<grid, STFT_THREADS, smem, stream>>>(wave, n_clips, length, clip_stride, center, (int)T, tiles_per_clip, out);

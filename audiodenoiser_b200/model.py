@@ -61,6 +61,8 @@ class UNet(nn.Module):
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.profile = None      # set to a list to record (layer, kind, flops, start_event, end_event) per kernel call
+        self.launch_count = 0    # kernels launched by this module so far (bench.py's gpu_launches)
 
     # ------------------------------------------------------------------ packing
     def _version_key(self, device):
@@ -147,17 +149,37 @@ class UNet(nn.Module):
         ws = self._workspace(n, h, w, x.device)
         hs, wz = ws["hs"], ws["ws"]
 
+        prof = self.profile
+
+        def timed(layer, kind, flops, launches, fn, *args):
+            if prof is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            st = fn(*args)
+            if prof is not None:
+                e1.record()
+                prof.append((layer, kind, flops, e0, e1))
+            self.launch_count += launches
+            _lib.check(st, f"{fn.__name__}[{layer}]")
+
         def conv(layer, src0, c0, src1, c1, h1, w1, lvl, dst, pool=None):
             p = pk[layer]
-            st = lib.adn_conv3x3_bn_relu_bf16(src0.data_ptr(), c0, src1.data_ptr() if src1 is not None else 0, c1, h1, w1,
-                                              n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"], p["scale"].data_ptr(),
-                                              p["shift"].data_ptr(), dst.data_ptr(), pool.data_ptr() if pool is not None else 0, s)
-            _lib.check(st, f"adn_conv3x3_bn_relu_bf16[{layer}]")
+            flops = 2.0 * n * hs[lvl] * wz[lvl] * p["co"] * 9 * (c0 + c1)
+            if pool is None:
+                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
+                      src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],
+                      p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(), 0, s)
+            else:      # conv and pool are separate launches inside the C call: time them apart
+                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
+                      src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],
+                      p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(), 0, s)
+                timed(layer + ".pool", "maxpool", 0.0, 1, lib.adn_maxpool2x2_bf16, dst.data_ptr(), n, hs[lvl], wz[lvl], p["co"],
+                      pool.data_ptr(), s)
 
         # encoder (DownSampleLayer.forward, model.py:29-32)
         p = pk["downconv1.0"]
-        _lib.check(lib.adn_conv3x3_c1_bn_relu_bf16(x.data_ptr(), n, h, w, p["w"].data_ptr(), p["scale"].data_ptr(),
-                                                   p["shift"].data_ptr(), ws["a0"].data_ptr(), s), "adn_conv3x3_c1_bn_relu_bf16")
+        timed("downconv1.0", "conv3x3_c1", 2.0 * n * h * w * 64 * 9, 1, lib.adn_conv3x3_c1_bn_relu_bf16, x.data_ptr(), n, h, w,
+              p["w"].data_ptr(), p["scale"].data_ptr(), p["shift"].data_ptr(), ws["a0"].data_ptr(), s)
         conv("downconv1.3", ws["a0"], 64, None, 0, 0, 0, 0, ws["s0"], ws["p0"])
         ch = [64, 128, 256, 512, 1024]
         for l in (1, 2, 3):
@@ -170,19 +192,18 @@ class UNet(nn.Module):
         for i, l in enumerate((3, 2, 1, 0)):
             name = f"upconv{i + 1}"
             pu = pk[f"{name}.up"]
-            st = lib.adn_convt2x2_bf16(cur.data_ptr(), pu["ci"], n, hs[l + 1], wz[l + 1], pu["w"].data_ptr(), pu["co"],
-                                       pu["bias"].data_ptr(), ws[f"u{l}"].data_ptr(), s)
-            _lib.check(st, f"adn_convt2x2_bf16[{name}]")
+            timed(f"{name}.up", "convt2x2", 2.0 * n * hs[l + 1] * wz[l + 1] * pu["ci"] * 4 * pu["co"], 1, lib.adn_convt2x2_bf16,
+                  cur.data_ptr(), pu["ci"], n, hs[l + 1], wz[l + 1], pu["w"].data_ptr(), pu["co"], pu["bias"].data_ptr(),
+                  ws[f"u{l}"].data_ptr(), s)
             conv(f"{name}.0", ws[f"s{l}"], ch[l], ws[f"u{l}"], ch[l], 2 * hs[l + 1], 2 * wz[l + 1], l, ws[f"ua{l}"])
             if l > 0:
                 conv(f"{name}.3", ws[f"ua{l}"], ch[l], None, 0, 0, 0, l, ws[f"ub{l}"])
                 cur = ws[f"ub{l}"]
             else:
                 p = pk[f"{name}.3"]
-                st = lib.adn_conv3x3_bn_relu_head_f32(ws["ua0"].data_ptr(), 64, 0, 0, 0, 0, n, h, w, p["w"].data_ptr(), 64,
-                                                      p["scale"].data_ptr(), p["shift"].data_ptr(), pk["out"]["w"].data_ptr(),
-                                                      pk["out"]["b"].data_ptr(), out.data_ptr(), s)
-                _lib.check(st, "adn_conv3x3_bn_relu_head_f32")
+                timed(f"{name}.3+out", "conv3x3_head", 2.0 * n * h * w * 64 * (9 * 64 + 1), 1, lib.adn_conv3x3_bn_relu_head_f32,
+                      ws["ua0"].data_ptr(), 64, 0, 0, 0, 0, n, h, w, p["w"].data_ptr(), 64, p["scale"].data_ptr(),
+                      p["shift"].data_ptr(), pk["out"]["w"].data_ptr(), pk["out"]["b"].data_ptr(), out.data_ptr(), s)
 
     def forward(self, x):
         """UNet.forward, model.py:70-94 (eval-mode BatchNorm)."""

@@ -1,0 +1,86 @@
+"""End-to-end hot path on one GPU: noisy waveform -> |STFT| -> UNet -> inverse STFT / overlap-add.
+
+This is the batched composition of the three drop-in pieces (create_test_dataset.audio_to_spectrogram, model.UNet.forward,
+test.griffin_lim_reconstruction) with every intermediate resident in HBM and, for a fixed batch shape, the whole launch
+sequence captured in one CUDA graph.  Reconstruction uses a random unit phasor (seeded, generated on the device) exactly as
+the reference does (test.py:36), or the phasor the caller injects.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, spectral
+from .model import UNet
+
+
+class Denoiser:
+    def __init__(self, model: UNet, center: bool = True, seed: int = 0, use_graph: bool = True):
+        _lib.require_cuda()
+        self.model = model.eval()
+        self.center = bool(center)
+        self.seed = int(seed)
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
+        self.launches_per_call = None
+
+    def denoise(self, wave: torch.Tensor, phasor: torch.Tensor | None = None, return_spectrograms: bool = False):
+        """wave (N, L) float32 CUDA -> audio (N, 128*(T-1)) float32 CUDA.  With return_spectrograms also returns
+        (noisy_mag, denoised_mag), each (N, 257, T)."""
+        if not wave.is_cuda:
+            raise _lib.AdnError("Denoiser.denoise needs a CUDA tensor (no CPU fallback)")
+        if wave.dim() == 1:
+            wave = wave.unsqueeze(0)
+        wave = wave.float().contiguous()
+        key = (tuple(wave.shape), str(wave.device), phasor is not None)
+        if not self.use_graph:
+            mag = spectral.stft_mag_batched(wave, self.center)
+            den = self.model(mag.unsqueeze(1)).squeeze(1)
+            audio = spectral.istft_batched(den, phasor, seed=self.seed)
+            return (audio, mag, den) if return_spectrograms else audio
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(wave, phasor)
+            self._graphs = {key: g}            # one resident shape
+        g["wave"].copy_(wave, non_blocking=True)
+        if phasor is not None:
+            g["phasor"].copy_(phasor.to(torch.complex64), non_blocking=True)
+        g["graph"].replay()
+        if return_spectrograms:
+            return g["audio"], g["mag"], g["den"]
+        return g["audio"]
+
+    def _capture(self, wave, phasor):
+        dev = wave.device
+        static_wave = wave.clone()
+        static_ph = phasor.to(torch.complex64).clone() if phasor is not None else None
+        with torch.cuda.device(dev):
+            # warm-up on a side stream: lazy init (weight packing, workspace, func attributes) must not be captured
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    mag = spectral.stft_mag_batched(static_wave, self.center)
+                    den = self.model(mag.unsqueeze(1)).squeeze(1)
+                    audio = spectral.istft_batched(den, static_ph, seed=self.seed)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                mag = spectral.stft_mag_batched(static_wave, self.center)
+                den = self.model(mag.unsqueeze(1)).squeeze(1)
+                audio = spectral.istft_batched(den, static_ph, seed=self.seed)
+        return {"graph": graph, "wave": static_wave, "phasor": static_ph, "mag": mag, "den": den, "audio": audio}
+
+    # ------------------------------------------------------------------ host-buffer entry (what a script calls)
+    def denoise_host(self, wave_host: torch.Tensor, out_host: torch.Tensor | None = None, device=None) -> torch.Tensor:
+        """(N, L) float32 host tensor (pinned for full speed) -> (N, 128*(T-1)) float32 host tensor.  Host->device copy of
+        the input and device->host copy of the result are part of the call; returns after the stream has drained."""
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(dev):
+            wave = wave_host.to(dev, non_blocking=True)
+            audio = self.denoise(wave)
+            if out_host is None:
+                out_host = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
+            out_host.copy_(audio, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host
