@@ -169,7 +169,7 @@ static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64
     const int64_t T = adn_stft_num_frames(length, center);
     if (T < 0) return ADN_ERR_SHORT;
     if (n_clips == 0) return ADN_OK;
-    if (!wave || !out) return ADN_ERR_ARG;
+    if ((!wave && length > 0) || !out) return ADN_ERR_ARG;      // an empty centred clip still yields one zero frame
     if (T > (int64_t)1 << 30) return ADN_ERR_ARG;
     int st = check_device();
     if (st != ADN_OK) return st;

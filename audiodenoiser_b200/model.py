@@ -138,7 +138,8 @@ class UNet(nn.Module):
                 ws[f"p{l}"] = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), **bf)          # pooled
                 ws[f"u{l}"] = torch.empty((n, 2 * hs[l + 1], 2 * wsz[l + 1], ch[l]), **bf)  # up-sampled into level l
                 ws[f"ua{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
-                ws[f"ub{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
+                if l > 0:                      # level 0's second decoder conv feeds the fused 1x1 head instead
+                    ws[f"ub{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
         self._ws = {key: ws}          # keep one shape resident
         return ws
 

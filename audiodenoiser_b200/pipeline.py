@@ -24,34 +24,40 @@ class Denoiser:
         self.launches_per_call = None
 
     def denoise(self, wave: torch.Tensor, phasor: torch.Tensor | None = None, return_spectrograms: bool = False):
-        """wave (N, L) float32 CUDA -> audio (N, 128*(T-1)) float32 CUDA.  With return_spectrograms also returns
-        (noisy_mag, denoised_mag), each (N, 257, T)."""
-        if not wave.is_cuda:
-            raise _lib.AdnError("Denoiser.denoise needs a CUDA tensor (no CPU fallback)")
+        """wave (N, L) float32 -> audio (N, 128*(T-1)) float32 CUDA.  ``wave`` is a CUDA tensor, or a (pinned) host tensor
+        that is copied straight into the graph's input buffer.  With return_spectrograms also returns
+        (noisy_mag, denoised_mag), each (N, 257, T).  In graph mode the returned tensors are the graph's static output
+        buffers: they are overwritten by the next call with the same shape."""
         if wave.dim() == 1:
             wave = wave.unsqueeze(0)
-        wave = wave.float().contiguous()
-        key = (tuple(wave.shape), str(wave.device), phasor is not None)
+        if wave.dtype != torch.float32:
+            wave = wave.float()
         if not self.use_graph:
+            if not wave.is_cuda:
+                wave = wave.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+            wave = wave.contiguous()
             mag = spectral.stft_mag_batched(wave, self.center)
             den = self.model(mag.unsqueeze(1)).squeeze(1)
             audio = spectral.istft_batched(den, phasor, seed=self.seed)
             return (audio, mag, den) if return_spectrograms else audio
+        dev = wave.device if wave.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        key = (tuple(wave.shape), str(dev), phasor is not None, self.model._version_key(dev))
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(wave, phasor)
+            g = self._capture(wave.to(dev), phasor)
             self._graphs = {key: g}            # one resident shape
-        g["wave"].copy_(wave, non_blocking=True)
-        if phasor is not None:
-            g["phasor"].copy_(phasor.to(torch.complex64), non_blocking=True)
-        g["graph"].replay()
+        with torch.cuda.device(dev):
+            g["wave"].copy_(wave, non_blocking=True)
+            if phasor is not None:
+                g["phasor"].copy_(phasor.to(torch.complex64), non_blocking=True)
+            g["graph"].replay()
         if return_spectrograms:
             return g["audio"], g["mag"], g["den"]
         return g["audio"]
 
     def _capture(self, wave, phasor):
         dev = wave.device
-        static_wave = wave.clone()
+        static_wave = wave.contiguous().clone()
         static_ph = phasor.to(torch.complex64).clone() if phasor is not None else None
         with torch.cuda.device(dev):
             # warm-up on a side stream: lazy init (weight packing, workspace, func attributes) must not be captured
@@ -69,7 +75,10 @@ class Denoiser:
                 mag = spectral.stft_mag_batched(static_wave, self.center)
                 den = self.model(mag.unsqueeze(1)).squeeze(1)
                 audio = spectral.istft_batched(den, static_ph, seed=self.seed)
-        return {"graph": graph, "wave": static_wave, "phasor": static_ph, "mag": mag, "den": den, "audio": audio}
+        # the graph holds raw pointers into the model's packed weights and activation workspace: keep them alive here even if
+        # the model later repacks (new checkpoint) or switches to another input shape
+        keep = (self.model._packed, dict(self.model._ws))
+        return {"graph": graph, "wave": static_wave, "phasor": static_ph, "mag": mag, "den": den, "audio": audio, "keep": keep}
 
     # ------------------------------------------------------------------ host-buffer entry (what a script calls)
     def denoise_host(self, wave_host: torch.Tensor, out_host: torch.Tensor | None = None, device=None) -> torch.Tensor:
@@ -77,8 +86,7 @@ class Denoiser:
         the input and device->host copy of the result are part of the call; returns after the stream has drained."""
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         with torch.cuda.device(dev):
-            wave = wave_host.to(dev, non_blocking=True)
-            audio = self.denoise(wave)
+            audio = self.denoise(wave_host)
             if out_host is None:
                 out_host = torch.empty(audio.shape, dtype=torch.float32, pin_memory=True)
             out_host.copy_(audio, non_blocking=True)

@@ -1,0 +1,128 @@
+"""Clip-level sharding of the hot path across the GPUs of one box (BASELINE config 4).
+
+Every clip is independent through STFT -> eval-mode UNet -> iSTFT (model.py has no cross-sample op), so the path
+shards with NO data-path collective: rank r owns the contiguous block ``shard_range(N, G, r)``.  NCCL is used only
+after the fact, as BASELINE.json's north_star asks: one all-gather of the denoised outputs and one all-reduce(SUM) of
+the partial error sums (so SNR / L1 are exact for unequal shards -- the reference's metrics are full-batch means,
+loss.py:86).  The helpers take a ``torch.distributed`` process group and work on whatever device the tensors live on,
+which lets the host logic be tested with the gloo backend on CPU (tests/test_sharding_gloo.py).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous block of ceil(N/G) items for ``rank`` (the last ranks may get fewer, or none)."""
+    if world_size < 1 or not (0 <= rank < world_size) or n_items < 0:
+        raise ValueError("bad shard request")
+    per = -(-n_items // world_size)
+    lo = min(rank * per, n_items)
+    return lo, min(lo + per, n_items)
+
+
+def shard_sizes(n_items: int, world_size: int) -> list[int]:
+    return [hi - lo for lo, hi in (shard_range(n_items, world_size, r) for r in range(world_size))]
+
+
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Gather the row-sharded ``local`` (n_r, ...) of every rank into (n_total, ...) on every rank, in rank order.
+
+    Shards follow ``shard_range``: equal blocks of ceil(N/G) rows except the tail.  One ``all_gather_into_tensor`` on a
+    padded (G*per, ...) buffer; the padding rows of the tail ranks are dropped by the final slice (a view)."""
+    world, rank = _world(group)
+    if world == 1:
+        if local.shape[0] != n_total:
+            raise ValueError("single-rank gather: local rows != n_total")
+        return local
+    per = -(-n_total // world)
+    lo, hi = shard_range(n_total, world, rank)
+    if local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank}: expected {hi - lo} local rows, got {local.shape[0]}")
+    tail = tuple(local.shape[1:])
+    if out is None:
+        out = torch.empty((world * per,) + tail, dtype=local.dtype, device=local.device)
+    elif tuple(out.shape) != (world * per,) + tail or out.dtype != local.dtype:
+        raise ValueError("out must be (world*ceil(N/world), ...) of the local dtype")
+    if local.shape[0] == per:
+        src = local.contiguous()
+    else:                                   # tail rank: pad to the common block size
+        src = torch.zeros((per,) + tail, dtype=local.dtype, device=local.device)
+        src[: local.shape[0]].copy_(local)
+    dist.all_gather_into_tensor(out, src, group=group)
+    return out[:n_total]
+
+
+def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place all-reduce(SUM) of a small float64 vector of partial sums / counts."""
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    return sums
+
+
+def stats_from_sums(sums) -> dict:
+    """[sum|target-pred|, sum target^2, sum (target-pred)^2, count] -> {'l1', 'snr_db', 'count'}.
+    SNR = 10 log10(sum target^2 / sum err^2) on magnitude spectrograms (the reference defines none)."""
+    s_abs, s_sig, s_err, cnt = (float(v) for v in sums[:4])
+    l1 = s_abs / cnt if cnt > 0 else float("nan")
+    snr = 10.0 * math.log10(s_sig / s_err) if s_err > 0 and s_sig > 0 else float("inf")
+    return {"l1": l1, "snr_db": snr, "count": int(cnt)}
+
+
+class ShardedDenoiser:
+    """One rank's view of the clip-sharded job: denoise the local shard with the single-GPU ``Denoiser``, then gather
+    outputs and reduce the error statistics over the group."""
+
+    def __init__(self, denoiser, group=None):
+        self.denoiser = denoiser
+        self.group = group
+        self.world, self.rank = _world(group)
+        self._gather_buf = None
+        self._sums = None
+
+    def local_range(self, n_total: int) -> tuple[int, int]:
+        return shard_range(n_total, self.world, self.rank)
+
+    def error_sums(self, pred_mag: torch.Tensor, target_mag: torch.Tensor) -> torch.Tensor:
+        """Device float64 [sum|d|, sum t^2, sum d^2, count] of this rank's shard (CUDA kernel adn_spec_error_sums_f64)."""
+        from . import _lib
+        if not pred_mag.is_cuda:
+            raise _lib.AdnError("error_sums needs CUDA tensors (no CPU fallback)")
+        if self._sums is None or self._sums.device != pred_mag.device:
+            self._sums = torch.zeros(4, dtype=torch.float64, device=pred_mag.device)
+        self._sums.zero_()
+        p = pred_mag.float().contiguous(); t = target_mag.float().contiguous()
+        if p.shape != t.shape:
+            raise ValueError("pred and target must have the same shape")
+        with torch.cuda.device(p.device):
+            st = _lib.load().adn_spec_error_sums_f64(p.data_ptr(), t.data_ptr(), p.numel(), self._sums.data_ptr(), _lib.stream_ptr())
+        _lib.check(st, "adn_spec_error_sums_f64")
+        self._sums[3] = float(p.numel())
+        return self._sums
+
+    def step(self, wave_local: torch.Tensor, n_total: int, target_mag_local: torch.Tensor | None = None, gather: bool = True):
+        """Denoise this rank's clips; returns (audio, sums): ``audio`` is the gathered (n_total, samples) tensor when
+        ``gather`` (every rank gets it, rank order = clip order) else the local shard; ``sums`` is the group-reduced
+        float64 statistics vector (None without a target)."""
+        if target_mag_local is not None:
+            audio, _mag, den = self.denoiser.denoise(wave_local, return_spectrograms=True)
+            sums = all_reduce_sums(self.error_sums(den, target_mag_local), self.group)
+        else:
+            audio, sums = self.denoiser.denoise(wave_local), None
+        if gather and self.world > 1:
+            per = -(-n_total // self.world)
+            shape = (self.world * per,) + tuple(audio.shape[1:])
+            if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != audio.device:
+                self._gather_buf = torch.empty(shape, dtype=audio.dtype, device=audio.device)
+            audio = all_gather_rows(audio, n_total, self.group, out=self._gather_buf)
+        return audio, sums

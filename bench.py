@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json): audio-seconds denoised per second through
+STFT -> UNet -> iSTFT on N B200s, with the kernel roofline and the reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--variant B|R] [--batch 64]
+
+One "step" = one pass of the hot path over one batch of synthetic clips per GPU (BASELINE config 3: batch 64, end-to-end
+STFT -> net -> iSTFT; clips are 3 s @ 44.1 kHz = 132 300 samples -> (257,1034) spectrograms, variant "B", or the
+reference-faithful 3 s @ 8 kHz = 24 000 samples -> (257,188), variant "R").  For N > 1 (torchrun, one rank per GPU)
+every rank denoises its own shard (weak scaling) and the step ends with the NCCL all-gather of the denoised audio and
+the all-reduce of the error statistics (BASELINE config 4).
+
+JSON keys: see the driver contract.  `value` = device-timed whole-job throughput with inputs resident in HBM;
+`e2e` = the same through Denoiser.denoise_host with pinned HOST buffers (H2D + D2H inside the timed region);
+`roofline` = the tcgen05 implicit-GEMM conv kernel (the dominant kernel) against the measured bf16 peak;
+`kernels` = per-kernel achieved figures incl. the STFT / iSTFT HBM GB/s; `cpu_baseline` = the CPU oracle chain
+(the arithmetic the reference executes) on a bounded sample on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio-sec/sec denoised (STFT->net->iSTFT)"
+UNIT = "audio-s/s"
+CLIP_SECONDS = 3.0
+GL_ITERATIONS = 50          # test.py:29 default
+
+
+def unet_flops(h: int, w: int) -> float:
+    """FLOPs of one UNet forward on a (1,1,h,w) input (conv 2*Ci*Co*9*H*W, convT 2*Ci*Co*4*Hin*Win, head 2*64*H*W)."""
+    hs, ws = [h], [w]
+    for _ in range(4):
+        hs.append(hs[-1] // 2); ws.append(ws[-1] // 2)
+    ch = [64, 128, 256, 512, 1024]
+    f = 0.0
+    cin = 1
+    for l in range(5):
+        f += 2.0 * 9 * hs[l] * ws[l] * (cin * ch[l] + ch[l] * ch[l])
+        cin = ch[l]
+    for l in (3, 2, 1, 0):
+        f += 2.0 * 4 * hs[l + 1] * ws[l + 1] * ch[l + 1] * ch[l]                    # ConvTranspose2d
+        f += 2.0 * 9 * hs[l] * ws[l] * (2 * ch[l] * ch[l] + ch[l] * ch[l])          # cat -> conv, conv
+    f += 2.0 * 64 * h * w
+    return f
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_burst": float(d["bf16_tflops"]),
+                    "bf16_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+        except Exception:  # noqa: BLE001
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU every 100 ms while a timed region runs (NVML)."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    NOTE = {"sw_power_cap": 0x4, "hw_power_brake": 0x80}
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference chain
+def cpu_reference_chain(waves, sd, threads: int):
+    """The reference's CPU path for these clips, as the oracle restates it: librosa-style float64 STFT magnitude
+    (create_test_dataset.py:39-40) -> model.py fp32 forward on torch CPU (test.py:112-113) -> griffin_lim_reconstruction
+    with its literal 50 x (istft, stft) loop (test.py:29-48).  Returns seconds."""
+    import numpy as np
+    import torch
+    from oracle import stft_oracle, unet_oracle
+    torch.set_num_threads(threads)
+    t0 = time.perf_counter()
+    mags = np.stack([stft_oracle.stft_mag(w, True) for w in waves]).astype(np.float32)
+    with torch.no_grad():
+        den = unet_oracle.unet_forward(sd, torch.from_numpy(mags).unsqueeze(1)).squeeze(1).numpy()
+    for d in den:
+        stft_oracle.griffin_lim_reconstruction(d, 512, 128, iterations=GL_ITERATIONS)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  The reference is
+    pure Python over librosa / torch; librosa is absent from this image, so the arm runs the oracle port (numpy/scipy
+    restatement of the librosa arithmetic + the torch-CPU UNet), with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import torch
+    from audiodenoiser_b200 import synth
+    from audiodenoiser_b200.checkpoint import seeded_state_dict
+    cores = os.cpu_count() or 1
+    sd = seeded_state_dict(7)
+    per_step = max(1, args.ref_clips)
+    n = per_step * (args.steps + args.warmup)
+    clips = [synth.make_clip(i, args.variant) for i in range(min(n, 4))]
+    steps = []
+    for s in range(args.warmup + args.steps):
+        waves = [clips[(s * per_step + j) % len(clips)] for j in range(per_step)]
+        dt = cpu_reference_chain(waves, sd, cores)
+        if s >= args.warmup:
+            steps.append(dt)
+    total = float(np.sum(steps))
+    value = per_step * args.steps * CLIP_SECONDS / total
+    t_frames = 1 + synth.VARIANTS[args.variant][1] // 128
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 STFT/iSTFT + f32 UNet (CPU)", "data": "synthetic",
+        "config": workload_config(args, t_frames, args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} clip(s)/step x {args.steps} steps, variant {args.variant}: float64 STFT -> fp32 torch-CPU UNet "
+                                   f"({torch.get_num_threads()} threads) -> {GL_ITERATIONS}-iteration istft/stft loop + istft"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, t_frames, batch):
+    sr, length = {"B": (44100, 132300), "R": (8000, 24000)}[args.variant]
+    return {"workload": f"BASELINE config 3/4: end-to-end STFT->UNet->iSTFT, batch {batch} clips per GPU per step, "
+                        f"3 s @ {sr} Hz synthetic tone/music + white/pink noise @ 8 dB",
+            "variant": args.variant, "clip_samples": length, "spectrogram": [257, t_frames], "batch_per_gpu": batch,
+            "n_fft": 512, "hop": 128, "weights": "random-init UNet (seeded He init, randomised BN statistics), 31.04 M params",
+            "parallelism": f"clip-sharded dp{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from audiodenoiser_b200 import _lib, sharding, spectral, synth
+    from audiodenoiser_b200.checkpoint import seeded_state_dict
+    from audiodenoiser_b200.model import UNet
+    from audiodenoiser_b200.pipeline import Denoiser
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _lib.require_cuda()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+    n_gpus = world
+    _lib.check(_lib.load().adn_device_check(), "adn_device_check")
+
+    batch = args.batch
+    sr, length = synth.VARIANTS[args.variant]
+    t_frames = spectral.num_frames(length, True)
+    n_out = 128 * (t_frames - 1)
+    peaks = measured_peaks()
+
+    sd = seeded_state_dict(7)
+    net = UNet().eval()
+    net.load_state_dict(sd)
+    den = Denoiser(net, center=True, seed=1234 + rank, use_graph=True)
+    job = sharding.ShardedDenoiser(den)
+
+    # synthetic inputs: `rot` distinct device-resident batches so successive steps never re-read a cached input
+    rot = args.rotate
+    uniq = min(batch, 16)
+    host_batches, clean_mags = [], []
+    for r in range(rot):
+        noisy, clean = [], []
+        for i in range(uniq):
+            a, b = synth.make_clip((rank * rot + r) * uniq + i, args.variant, return_clean=True)
+            noisy.append(a); clean.append(b)
+        idx = [i % uniq for i in range(batch)]
+        gain = np.array([1.0 - 0.25 * ((i // uniq) % 3) / 3.0 for i in range(batch)], np.float32)[:, None]
+        host_batches.append(torch.from_numpy(np.stack(noisy)[idx] * gain).pin_memory())
+        clean_mags.append(spectral.stft_mag_batched(torch.from_numpy(np.stack(clean)[idx] * gain).to(dev), True))
+    dev_batches = [h.to(dev) for h in host_batches]
+    host_out = torch.empty((batch, n_out), dtype=torch.float32).pin_memory()
+    n_total = batch * n_gpus
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device(i):
+        audio, sums = job.step(dev_batches[i % rot], n_total, clean_mags[i % rot], gather=True)
+        return audio, sums
+
+    def step_host(i):
+        wave = host_batches[i % rot].to(dev, non_blocking=True)
+        audio, sums = job.step(wave, n_total, clean_mags[i % rot], gather=True)
+        lo = rank * batch
+        host_out.copy_(audio[lo:lo + batch], non_blocking=True)
+        stats = sums.cpu()                      # device -> host read of the step's statistics (synchronises)
+        return stats
+
+    def timed(fn, steps, warmup, sampler):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            e0.record()
+            for i in range(steps):
+                fn(warmup + i)
+            e1.record()
+            barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    sampler = ClockSampler(local_rank)
+    launches0 = net.launch_count
+    ms_dev = timed(step_device, args.steps, args.warmup, sampler)
+    clocks = sampler.summary()
+    ms_e2e = timed(step_host, args.steps, args.warmup, ClockSampler(local_rank))
+    audio, sums = step_device(0)
+    stats = sharding.stats_from_sums(sums.cpu())
+    barrier()
+
+    audio_s_per_step = n_total * CLIP_SECONDS
+    value = audio_s_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = audio_s_per_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel figures, eager mode with CUDA events around every launch (same stream as the launches)
+    kernels, roofline, launches_per_step = {}, None, None
+    if rank == 0 or True:
+        net.profile = []
+        eager = Denoiser(net, center=True, seed=1234 + rank, use_graph=False)
+        reps = max(2, min(args.steps, 5))
+        spans = {"stft": [], "istft": []}
+        lc0 = net.launch_count
+        for i in range(2 + reps):
+            if i == 2:
+                net.profile = []
+                lc0 = net.launch_count
+            w = dev_batches[i % rot]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record(); mag = spectral.stft_mag_batched(w, True); ev[1].record()
+            dmag = net(mag.unsqueeze(1)).squeeze(1)
+            ev[2].record(); spectral.istft_batched(dmag, None, seed=i); ev[3].record()
+            if i >= 2:
+                spans["stft"].append((ev[0], ev[1])); spans["istft"].append((ev[2], ev[3]))
+        torch.cuda.synchronize()
+        launches_per_step = (net.launch_count - lc0) // reps + 2 + 1        # + stft + istft + error-sums kernel
+        prof = net.profile
+        net.profile = None
+        agg = {}
+        for layer, kind, flops, a, b in prof:
+            d = agg.setdefault(kind, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += a.elapsed_time(b); d["flops"] += flops; d["launches"] += 1
+        per_layer = {}
+        for layer, kind, flops, a, b in prof:
+            d = per_layer.setdefault(layer, {"ms": 0.0, "flops": 0.0, "n": 0})
+            d["ms"] += a.elapsed_time(b); d["flops"] += flops; d["n"] += 1
+        tc = {"ms": 0.0, "flops": 0.0, "launches": 0}
+        for kind in ("conv3x3", "convt2x2", "conv3x3_head"):
+            if kind in agg:
+                for k in tc:
+                    tc[k] += agg[kind][k]
+        tc_tflops = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
+        peak_tc = peaks["bf16_sustained"]
+        roofline = {"kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv3x3 / convT2x2 / conv3x3+head)", "bound": "tensor",
+                    "achieved": tc_tflops, "peak": peak_tc, "unit": "TFLOP/s", "frac": tc_tflops / peak_tc,
+                    "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+                    "launches_per_step": tc["launches"] // reps, "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),
+                    "algorithmic_flops_per_step": tc["flops"] / reps, "traffic": None}
+        stft_ms = float(np.mean([a.elapsed_time(b) for a, b in spans["stft"]]))
+        istft_ms = float(np.mean([a.elapsed_time(b) for a, b in spans["istft"]]))
+        stft_bytes = batch * (4 * length + 4 * 257 * t_frames)
+        istft_bytes = batch * (4 * 257 * t_frames + 4 * n_out)           # magnitude in, device-generated phase, audio out
+        kernels = {
+            "stft_mag": {"ms": stft_ms, "bytes": stft_bytes, "GBps": stft_bytes / stft_ms / 1e6, "frac_of_hbm": stft_bytes / stft_ms / 1e6 / peaks["hbm_gbs"]},
+            "istft_ola": {"ms": istft_ms, "bytes": istft_bytes, "GBps": istft_bytes / istft_ms / 1e6, "frac_of_hbm": istft_bytes / istft_ms / 1e6 / peaks["hbm_gbs"]},
+        }
+        for kind, d in agg.items():
+            kernels[kind] = {"ms_per_step": d["ms"] / reps, "launches_per_step": d["launches"] // reps,
+                             "TFLOPs": (d["flops"] / (d["ms"] * 1e-3) / 1e12) if d["flops"] else None}
+        if args.layers:
+            kernels["layers"] = {k: {"ms": v["ms"] / v["n"], "TFLOPs": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] else None}
+                                 for k, v in per_layer.items()}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload through the oracle chain
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        waves = [host_batches[0][i].numpy() for i in range(args.ref_clips)]
+        cpu_reference_chain(waves[:1], sd, cores)                       # warm-up (thread pools, oneDNN primitives)
+        dt = cpu_reference_chain(waves, sd, cores)
+        cpu_baseline = {"value": len(waves) * CLIP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{len(waves)} clip(s) of the same batch, variant {args.variant}: float64 numpy/scipy STFT -> fp32 torch-CPU "
+                                  f"UNet -> {GL_ITERATIONS}-iteration istft/stft loop + istft; {dt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {**workload_config(args, t_frames, batch),
+                       "l2": f"inputs rotate over {rot} resident batches; every step rewrites ~{unet_workspace_gb(batch, 257, t_frames):.1f} GB of activations (>> 126 MB L2)",
+                       "collectives": "all_gather(audio) + all_reduce(error sums) per step" if n_gpus > 1 else "none (single GPU)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(batch * length * 4) * n_gpus, "d2h_bytes_per_step": int(batch * n_out * 4 + 32) * n_gpus},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": kernels,
+            "unet_flops_per_clip": unet_flops(257, t_frames),
+            "unet_tflops_in_step": unet_flops(257, t_frames) * batch / (ms_dev / args.steps * 1e-3) / 1e12,
+            "quality": {"snr_db_vs_clean_mag": stats["snr_db"], "l1_vs_clean_mag": stats["l1"], "note": "random-init weights: numbers only prove the statistics path runs"},
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def unet_workspace_gb(n, h, w):
+    hs, ws = [h], [w]
+    for _ in range(4):
+        hs.append(hs[-1] // 2); ws.append(ws[-1] // 2)
+    ch = [64, 128, 256, 512, 1024]
+    total = 0
+    for l in range(5):
+        total += (2 if l == 4 else 4) * n * hs[l] * ws[l] * ch[l] * 2
+        if l < 4:
+            total += n * hs[l + 1] * ws[l + 1] * ch[l] * 2
+    return total / 1e9
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="B", choices=["B", "R"], help="B: 3 s @ 44.1 kHz (BASELINE-literal); R: 3 s @ 8 kHz (what the reference scripts feed)")
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--rotate", type=int, default=4, help="distinct resident input batches")
+    ap.add_argument("--ref-clips", type=int, default=1, help="clips per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="add per-layer timings to the JSON line")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

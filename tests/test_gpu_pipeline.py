@@ -1,0 +1,60 @@
+"""End-to-end hot path on one GPU (waveform -> |STFT| -> UNet -> iSTFT) against the CPU oracle chain, and the CUDA-graph
+path against the eager path."""
+import numpy as np
+import pytest
+import torch
+
+from audiodenoiser_b200 import synth
+from audiodenoiser_b200.checkpoint import seeded_state_dict
+from audiodenoiser_b200.model import UNet
+from audiodenoiser_b200.pipeline import Denoiser
+from oracle import stft_oracle as so, unet_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def net():
+    m = UNet().eval()
+    m.load_state_dict(seeded_state_dict(7))
+    return m
+
+
+def test_end_to_end_matches_oracle_chain(net):
+    sd = seeded_state_dict(7)
+    x = np.stack([synth.make_clip(i, "R") for i in range(2)])
+    rng = np.random.default_rng(0)
+    ang = np.exp(2j * np.pi * rng.random((2, 257, 188)))
+    den = Denoiser(net, center=True, use_graph=False)
+    audio, mag, dmag = den.denoise(torch.from_numpy(x).to(dev()), torch.from_numpy(ang.astype(np.complex64)).to(dev()),
+                                   return_spectrograms=True)
+    ref_mag = np.stack([so.stft_mag(xi.astype(np.float64), True) for xi in x]).astype(np.float32)
+    ref_den = unet_oracle.unet_forward(sd, torch.from_numpy(ref_mag).unsqueeze(1)).squeeze(1).numpy()
+    ref_audio = np.stack([so.istft(ref_den[i].astype(np.float64) * ang[i]) for i in range(2)])
+    assert np.max(np.abs(mag.cpu().numpy() - ref_mag)) <= 1e-4 * np.max(np.abs(ref_mag))
+    nrel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert nrel(dmag.cpu().numpy().astype(np.float64), ref_den) <= 1e-2
+    assert audio.shape == (2, 23936)
+    assert nrel(audio.cpu().numpy().astype(np.float64), ref_audio) <= 1e-2
+
+
+def test_graph_replay_equals_eager(net):
+    x = torch.from_numpy(np.stack([synth.make_clip(i, "R") for i in range(3)])).to(dev())
+    eager = Denoiser(net, seed=11, use_graph=False).denoise(x)
+    g = Denoiser(net, seed=11, use_graph=True)
+    a = g.denoise(x).clone()
+    b = g.denoise(x * 0.5).clone()
+    c = g.denoise(x).clone()
+    assert torch.equal(a, eager) and torch.equal(a, c) and not torch.equal(a, b)
+
+
+def test_denoise_host_buffers(net):
+    x = torch.from_numpy(np.stack([synth.make_clip(i, "R") for i in range(2)])).pin_memory()
+    d = Denoiser(net, seed=3)
+    out = d.denoise_host(x)
+    assert out.shape == (2, 23936) and not out.is_cuda
+    assert torch.equal(out, d.denoise(x.to(dev())).cpu())

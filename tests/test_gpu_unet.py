@@ -1,0 +1,175 @@
+"""Parity of the tcgen05 UNet forward (through the C ABI) against the reference's own model.py outputs
+(tests/golden/unet_*.npz, made by oracle/make_golden.py from /root/reference/code/model.py) and the fp32 oracle.
+
+Tolerance (BASELINE.json north_star): bf16 model output within 1e-2 relative error -- norm-wise ||d|| / ||ref||
+ -- and output SNR within 0.05 dB."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from audiodenoiser_b200 import _lib
+from audiodenoiser_b200.checkpoint import seeded_state_dict
+from audiodenoiser_b200.model import UNet
+from oracle import unet_oracle
+
+pytestmark = pytest.mark.gpu
+UNET_TOL = 1e-2
+SNR_TOL_DB = 0.05
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def nrel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def to_nhwc_bf16(x):
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def from_nhwc(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.fixture(scope="module")
+def net():
+    m = UNet().eval()
+    m.load_state_dict(seeded_state_dict(7))
+    return m
+
+
+@pytest.mark.parametrize("n,c0,c1,co,h,w", [(2, 64, 0, 64, 20, 19), (1, 64, 0, 128, 37, 26), (2, 128, 0, 256, 9, 6),
+                                            (1, 256, 256, 256, 16, 11), (2, 64, 64, 64, 33, 28), (1, 512, 0, 1024, 4, 3),
+                                            (1, 512, 512, 512, 5, 7), (3, 64, 0, 64, 257, 188), (1, 64, 0, 64, 1, 1)])
+def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
+    """One implicit-GEMM conv against F.conv2d on the same bf16-rounded operands: only accumulation order and the
+    final bf16 store differ, so the bound is tight (output rounding 2^-9 max-wise)."""
+    lib = _lib.load(); s = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(1000 * h + w)
+    ci = c0 + c1
+    x0 = bf16_round(torch.randn(n, c0, h, w, generator=g))
+    h1, w1 = (max(h - (h % 2), 1), max(w - (w % 2), 1)) if c1 else (0, 0)
+    x1 = bf16_round(torch.randn(n, c1, h1, w1, generator=g)) if c1 else None
+    wt = bf16_round(torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (9 * ci)) ** 0.5)
+    scale = 0.5 + torch.rand(co, generator=g); shift = 0.1 * torch.randn(co, generator=g)
+    xin = x0 if x1 is None else torch.cat([x0, F.pad(x1, [0, w - w1, 0, h - h1])], 1)
+    ref = F.relu(F.conv2d(xin, wt, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    wp = torch.empty((co, 9, ci), dtype=torch.bfloat16, device=dev())
+    wd = wt.to(dev()).contiguous()
+    _lib.check(lib.adn_pack_conv3x3_weight_bf16(wd.data_ptr(), co, ci, wp.data_ptr(), s))
+    a0 = to_nhwc_bf16(x0).to(dev()); a1 = to_nhwc_bf16(x1).to(dev()) if c1 else None
+    out = torch.zeros((n, h, w, co), dtype=torch.bfloat16, device=dev())
+    do_pool = h >= 2 and w >= 2
+    pool = torch.zeros((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=dev()) if do_pool else None
+    sc, sh = scale.to(dev()), shift.to(dev())
+    _lib.check(lib.adn_conv3x3_bn_relu_bf16(a0.data_ptr(), c0, a1.data_ptr() if c1 else 0, c1, h1, w1, n, h, w, wp.data_ptr(), co,
+                                            sc.data_ptr(), sh.data_ptr(), out.data_ptr(), pool.data_ptr() if do_pool else 0, s))
+    torch.cuda.synchronize()
+    got = from_nhwc(out.cpu())
+    assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+    assert nrel(got, ref) <= 2.5e-3
+    if do_pool:
+        assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))         # pooling of the stored values is exact
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
+def test_convt2x2(n, ci, co, h, w):
+    lib = _lib.load(); s = _lib.stream_ptr()
+    g = torch.Generator().manual_seed(ci + h)
+    x = bf16_round(torch.randn(n, ci, h, w, generator=g))
+    wt = bf16_round(torch.randn(ci, co, 2, 2, generator=g) * (1.0 / ci) ** 0.5)
+    b = 0.1 * torch.randn(co, generator=g)
+    ref = F.conv_transpose2d(x, wt, b, stride=2)
+    wp = torch.empty((4, co, ci), dtype=torch.bfloat16, device=dev())
+    wd = wt.to(dev()).contiguous()
+    _lib.check(lib.adn_pack_convt2x2_weight_bf16(wd.data_ptr(), ci, co, wp.data_ptr(), s))
+    a = to_nhwc_bf16(x).to(dev()); bd = b.to(dev())
+    out = torch.zeros((n, 2 * h, 2 * w, co), dtype=torch.bfloat16, device=dev())
+    _lib.check(lib.adn_convt2x2_bf16(a.data_ptr(), ci, n, h, w, wp.data_ptr(), co, bd.data_ptr(), out.data_ptr(), s))
+    torch.cuda.synchronize()
+    got = from_nhwc(out.cpu())
+    assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("name", ["small", "train", "test"])
+def test_unet_matches_reference_fixture(net, golden_dir, name):
+    z = np.load(os.path.join(golden_dir, f"unet_{name}.npz"))
+    y = net(torch.from_numpy(z["x"]).to(dev()))
+    assert y.shape == z["y"].shape and y.dtype == torch.float32 and y.is_cuda
+    y = y.cpu().numpy()
+    assert nrel(y, z["y"]) <= UNET_TOL
+    # output SNR of the "denoised" magnitude against a target, reference-fp32 model vs this build
+    clean = 0.5 * z["x"]
+    snr = lambda d: 10.0 * np.log10(np.sum(clean.astype(np.float64) ** 2) / np.sum((clean.astype(np.float64) - d) ** 2))
+    assert abs(snr(y) - snr(z["y"])) <= SNR_TOL_DB
+
+
+def test_unet_intermediate_levels(net):
+    """Per-level parity against the oracle's intermediates: localises an error to a layer."""
+    sd = seeded_state_dict(7)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "unet_small.npz"))
+    x = torch.from_numpy(z["x"])
+    _, inter = unet_oracle.unet_forward(sd, x, return_intermediates=True)
+    net(x.to(dev())); torch.cuda.synchronize()
+    ws = list(net._ws.values())[0]
+    names = {"down1": "s0", "down2": "s1", "down3": "s2", "down4": "s3", "bottle": "s4", "up1": "ub3", "up2": "ub2", "up3": "ub1"}
+    for k, b in names.items():
+        assert nrel(from_nhwc(ws[b].cpu()).numpy(), inter[k].numpy()) <= UNET_TOL, k
+
+
+def test_concat_order_and_pad_side(net):
+    """model.py:49 cat([skip, up]) and model.py:44-47 pad right/bottom: zeroing the skip half of upconv4's first conv
+    must match the oracle doing the same (odd 257 x 47 input exercises both pads)."""
+    sd = seeded_state_dict(7)
+    sd["upconv4.conv.double_conv.0.weight"][:, :64] = 0
+    sd["upconv1.conv.double_conv.0.weight"][:, 512:] *= 2
+    m = UNet().eval(); m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 1, 257, 47, generator=g) * 3
+    ref = unet_oracle.unet_forward(sd, x).numpy()
+    assert nrel(m(x.to(dev())).cpu().numpy(), ref) <= UNET_TOL
+
+
+def test_state_dict_round_trip_and_repack(net):
+    sd = seeded_state_dict(7)
+    got = net.state_dict()
+    assert list(got.keys()) == list(sd.keys()) and len(got) == 136
+    for k in sd:
+        assert got[k].dtype == sd[k].dtype and torch.equal(got[k].cpu(), sd[k])
+    # a new checkpoint loaded into the same module must repack (no stale bf16 weights)
+    m = UNet().eval(); m.load_state_dict(sd)
+    x = torch.rand(1, 1, 64, 32) * 2
+    y7 = m(x.to(dev())).cpu()
+    sd3 = seeded_state_dict(3)
+    m.load_state_dict(sd3)
+    y3 = m(x.to(dev())).cpu().numpy()
+    assert nrel(y3, unet_oracle.unet_forward(sd3, x).numpy()) <= UNET_TOL
+    assert nrel(y7.numpy(), y3) > 0.05
+
+
+def test_batch_larger_than_chunk_and_batch_invariance(net):
+    """test.py:113 feeds the whole test set as one batch; results must not depend on the batch a clip sits in."""
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(70, 1, 32, 48, generator=g) * 2).to(dev())
+    y = net(x)
+    y1 = net(x[65:66])
+    assert torch.equal(y[65:66], y1)
+
+
+def test_input_validation(net):
+    with pytest.raises(_lib.AdnError):
+        net(torch.zeros(1, 1, 64, 64))
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 2, 64, 64, device=dev()))
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 1, 8, 8, device=dev()))
