@@ -1,0 +1,389 @@
+// conv_halo.cu -- Conv2d 3x3 (pad 1) + folded BatchNorm + ReLU of the reference UNet (code/model.py:11-16), the channel
+// concat + F.pad in front of the decoder convs (model.py:44-49) and the fused 1x1 head (model.py:68,93), as a persistent
+// warp-specialised tcgen05/TMEM implicit GEMM whose A operand is a HALO TILE RESIDENT IN SHARED MEMORY.
+//
+//   GEMM view   D[M = 128 pixels (16 rows x 8 cols), N = BLOCK_N] += A_tap[M, 64] * B_tap[N, 64]^T over 9 taps x Cin/64 chunks.
+//   A operand   one 4-D TMA box {64 ch, 16 px, 18 rows, 1 image} per 64-channel chunk = the tile plus its 1-pixel halo, rows
+//               pitched at 16 pixels (2048 B) so that every 8-pixel row segment is one 1024-byte SWIZZLE_128B atom group.
+//               The nine taps are nine UMMA descriptors INTO THE SAME TILE: start = base + (dy*16 + dx)*128 B, stride between
+//               8-row groups = 2048 B (the swizzle follows absolute smem address bits, so no base offset is needed).  Each input
+//               element is fetched from L2 once per tile instead of nine times -- the first version of this kernel
+//               (one TMA box per tap) ran the 64-channel full-resolution layers at the L2->SM bandwidth limit.
+//               Out-of-bounds rows / columns arrive as zeros = the conv's zero padding and the F.pad of the up-sampled map;
+//               the K range may span two tensors (skip, up): torch.cat is never materialised.
+//   B operand   packed weights [N][tap][Cin] bf16; per (tap, chunk) one 2-D TMA box {64, BLOCK_N}.  When the whole
+//               9*Cin x BLOCK_N panel fits beside the A ring (<= 147 KB) it is loaded ONCE per CTA and stays resident for
+//               every tile; otherwise it streams through its own ring.
+//   roles       warp 0: A producer - warp 1: tcgen05.mma issuer - warp 2: B producer + TMEM allocator - warps 3..6: epilogue
+//               (tcgen05.ld -> fp32 BN scale/shift -> ReLU -> bf16 NHWC store | fused 2x2 max-pool | fused 1x1 head).
+//               Two TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "tc_common.cuh"
+
+namespace adn {
+
+constexpr int H_TW = 8, H_TH = 16;                 // pixel tile: 16 rows x 8 columns = 128 GEMM rows
+constexpr int H_PITCH = 16;                        // halo row pitch in pixels (2048 B: a multiple of the 1024-B swizzle atom)
+constexpr int H_ROWS = H_TH + 2;
+constexpr int H_A_STAGE = H_ROWS * H_PITCH * 128;  // 36 864 B
+constexpr int H_THREADS = 224;
+constexpr int H_EPI_THREADS = 128;
+constexpr int H_MAX_A = 8, H_MAX_B = 16;
+
+enum { HEPI_NHWC = 0, HEPI_HEAD = 2 };
+
+struct HaloArgs {
+    int c0_chunks, c1_chunks;
+    int n_img, H, W;
+    int tiles_x, tiles_y;
+    int c_out, n_blocks, num_tiles;
+    int epi;
+    int a_stages, b_slots, b_resident;
+    const float* scale;
+    const float* shift;
+    __nv_bfloat16* out;
+    __nv_bfloat16* pool_out;       // optional fused MaxPool2d(2): (n, H/2, W/2, c_out)
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+};
+
+template <int BLOCK_N, bool B_RESIDENT>
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB, const HaloArgs a) {
+    constexpr int B_BLOCK = BLOCK_N * 128;                         // bytes of one (tap, chunk) weight block
+    constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + (uint32_t)a.a_stages * H_A_STAGE;
+    const uint32_t aux_off = (uint32_t)a.a_stages * H_A_STAGE + (uint32_t)a.b_slots * B_BLOCK;
+    float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);     // [c_out] all output channels, loaded once per CTA
+    float* s_shift = s_scale + a.c_out;
+    float* s_head = s_shift + a.c_out;
+    const uint32_t aux_f32 = (uint32_t)(2 * a.c_out + 64) * 4;
+    const uint32_t bar_base = smem_base + aux_off + aux_f32;
+    auto full_a = [&](int s) { return bar_base + 8u * s; };
+    auto empty_a = [&](int s) { return bar_base + 8u * (H_MAX_A + s); };
+    auto full_b = [&](int s) { return bar_base + 8u * (2 * H_MAX_A + s); };
+    auto empty_b = [&](int s) { return bar_base + 8u * (2 * H_MAX_A + H_MAX_B + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (2 * H_MAX_A + 2 * H_MAX_B + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (2 * H_MAX_A + 2 * H_MAX_B + 2 + s); };
+    const uint32_t bres = bar_base + 8u * (2 * H_MAX_A + 2 * H_MAX_B + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + aux_off + aux_f32 + (2 * H_MAX_A + 2 * H_MAX_B + 5) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < H_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < H_MAX_B; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), H_EPI_THREADS / 32); }
+        mbar_init(bres, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int chunks = a.c0_chunks + a.c1_chunks;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        // ===================================================================== A producer: one halo tile per (tile, chunk)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int m = tile / a.n_blocks;
+                const int img = m / tiles_per_img;
+                const int rem = m - img * tiles_per_img;
+                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+                const int x0 = tx * H_TW - 1, y0 = ty * H_TH - 1;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(empty_a(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_a(stage), H_A_STAGE);
+                    const uint32_t dst = a_base + (uint32_t)stage * H_A_STAGE;
+                    if (ch < a.c0_chunks) tma_load_4d(dst, &tmA0, full_a(stage), ch * 64, x0, y0, img);
+                    else tma_load_4d(dst, &tmA1, full_a(stage), (ch - a.c0_chunks) * 64, x0, y0, img);
+                    if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================================== B producer
+        if (lane == 0) {
+            if (B_RESIDENT) {
+                mbar_arrive_expect_tx(bres, (uint32_t)(9 * chunks) * B_BLOCK);
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int tap = 0; tap < 9; ++tap)
+                        tma_load_2d(b_base + (uint32_t)(ch * 9 + tap) * B_BLOCK, &tmB, bres, (tap * chunks + ch) * 64, 0);
+            } else {
+                int slot = 0; uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                    const int n_blk = tile % a.n_blocks;
+                    for (int ch = 0; ch < chunks; ++ch)
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(empty_b(slot), phase ^ 1u);
+                            mbar_arrive_expect_tx(full_b(slot), B_BLOCK);
+                            tma_load_2d(b_base + (uint32_t)slot * B_BLOCK, &tmB, full_b(slot), (tap * chunks + ch) * 64, n_blk * BLOCK_N);
+                            if (++slot == a.b_slots) { slot = 0; phase ^= 1u; }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer (whole warp, one elected lane issues)
+        // Descriptor arithmetic is hoisted: per stage one base descriptor, per tap / k-step a compile-time constant is added
+        // to the 14-bit start-address field (never carries: shared memory is < 256 KB).
+        constexpr uint32_t idesc = make_idesc(BLOCK_N);
+        constexpr uint64_t B_STEP = (uint64_t)(B_BLOCK >> 4);
+        int sa = 0; uint32_t pa = 0;
+        int sb = 0; uint32_t pb = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        if (B_RESIDENT) { mbar_wait(bres, 0); tc_fence_after(); }
+        const uint64_t db_base = make_sw128_desc(b_base);
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            mbar_wait(tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(full_a(sa), pa);
+                tc_fence_after();
+                // measured on B200: the UMMA swizzle is a function of the absolute shared-memory address bits (like TMA's), so
+                // a tap view that starts dx rows into a 1024-byte atom needs NO descriptor base offset
+                const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * H_A_STAGE, H_PITCH * 128);
+                if (B_RESIDENT) {
+                    const uint64_t db_chunk = db_base + (uint64_t)(ch * 9) * B_STEP;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
+                            const uint64_t db = db_chunk + (uint64_t)tap * B_STEP;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)                  // UMMA_K = 16: +32 bytes inside the swizzle row
+                                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                        }
+                        umma_commit(empty_a(sa));
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(full_b(sb), pb);
+                        tc_fence_after();
+                        const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
+                        const uint64_t db = db_base + (uint64_t)sb * B_STEP;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                            umma_commit(empty_b(sb));
+                            if (tap == 8) umma_commit(empty_a(sa));
+                        }
+                        __syncwarp();
+                        if (++sb == a.b_slots) { sb = 0; pb ^= 1u; }
+                    }
+                }
+                if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
+            }
+            if (elect_one()) umma_commit(tfull(acc));
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 3..6 = TMEM lane quadrants 3,0,1,2)
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                            // accumulator row = pixel within the tile
+        const int et = threadIdx.x - 96;                             // 0..127
+        const int lx = row & (H_TW - 1), ly = row >> 3;
+        if (a.epi == HEPI_HEAD && et < 64) s_head[et] = a.head_w[et];
+        for (int c = et; c < a.c_out; c += H_EPI_THREADS) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
+        named_bar_sync(1, H_EPI_THREADS);
+        const int Hp = a.H >> 1, Wp = a.W >> 1;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const int n_blk = tile % a.n_blocks;
+            const int m = tile / a.n_blocks;
+            const int img = m / tiles_per_img;
+            const int rem = m - img * tiles_per_img;
+            const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+            const int x = tx * H_TW + lx, y = ty * H_TH + ly;
+            const bool valid = (x < a.W) && (y < a.H);
+            // pooled pixel owned by this lane: lanes with even (lx, ly); its 2x2 window = lanes ^1, ^8, ^9 of the same warp
+            const bool pool_writer = a.pool_out && !(lx & 1) && !(ly & 1) && (x >> 1) < Wp && (y >> 1) < Hp;
+
+            const float* t_scale = s_scale + n_blk * BLOCK_N;
+            const float* t_shift = s_shift + n_blk * BLOCK_N;
+
+            mbar_wait(tfull(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            float head_acc = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(t_row + (uint32_t)c0, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(__uint_as_float(r[i]), t_scale[c0 + i], t_shift[c0 + i]), 0.f);
+                if (a.epi == HEPI_HEAD) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[c0 + i], head_acc);
+                } else {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        pk[i] = *reinterpret_cast<uint32_t*>(&p);
+                    }
+                    const int n = n_blk * BLOCK_N + c0;
+                    if (valid) {
+                        uint4* d4 = reinterpret_cast<uint4*>(a.out + (((long long)img * a.H + y) * a.W + x) * a.c_out + n);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    }
+                    if (a.pool_out) {                                 // warp-uniform
+                        // values are post-ReLU (>= 0) and rows outside the image are never read by a writer (floor pooling),
+                        // so a plain max over the 2x2 lane window is exact
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            __nv_bfloat162 m0 = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
+                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+                            m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&o1));
+                            uint32_t mm = *reinterpret_cast<uint32_t*>(&m0);
+                            uint32_t o8 = __shfl_xor_sync(0xffffffffu, mm, 8);
+                            m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&o8));
+                            pk[i] = *reinterpret_cast<uint32_t*>(&m0);
+                        }
+                        if (pool_writer) {
+                            uint4* d4 = reinterpret_cast<uint4*>(a.pool_out + (((long long)img * Hp + (y >> 1)) * Wp + (x >> 1)) * a.c_out + n);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                        }
+                    }
+                }
+            }
+            if (a.epi == HEPI_HEAD && valid)
+                a.head_out[((long long)img * a.H + y) * a.W + x] = head_acc + a.head_b[0];
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));                 // 4 arrivals (one per epilogue warp) free the accumulator
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+template <int BLOCK_N>
+static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, HaloArgs& args, int chunks,
+                       cudaStream_t stream) {
+    constexpr int B_BLOCK = BLOCK_N * 128;
+    const int AUX = (2 * args.c_out + 64) * 4 + (2 * H_MAX_A + 2 * H_MAX_B + 5) * 8 + 16;
+    constexpr int MAX_DYN = 232448;
+    const int budget = MAX_DYN - 1024 - AUX;
+    const int total_b = 9 * chunks * B_BLOCK;
+    if (args.n_blocks == 1 && total_b + 2 * H_A_STAGE <= budget) {
+        args.b_resident = 1;
+        args.b_slots = 9 * chunks;
+        int st = (budget - total_b) / H_A_STAGE;
+        args.a_stages = st > H_MAX_A ? H_MAX_A : st;
+    } else {
+        args.b_resident = 0;
+        args.a_stages = (BLOCK_N >= 256) ? 2 : 3;
+        int sl = (budget - args.a_stages * H_A_STAGE) / B_BLOCK;
+        args.b_slots = sl > H_MAX_B ? H_MAX_B : sl;
+        if (args.b_slots < 2) return ADN_ERR_ARG;
+    }
+    const int smem = 1024 + args.a_stages * H_A_STAGE + args.b_slots * B_BLOCK + AUX;
+    const int sms = num_sms();
+    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    if (args.b_resident) {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true>, MAX_DYN, smem_set));
+        conv3x3_halo_kernel<BLOCK_N, true><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, args);
+    } else {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false>, MAX_DYN, smem_set));
+        conv3x3_halo_kernel<BLOCK_N, false><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, args);
+    }
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
+                        const void* w_packed, int c_out, const float* scale, const float* shift, int epi, void* out, void* pool_out,
+                        const float* head_w, const float* head_b, float* head_out, cudaStream_t stream) {
+    if (!src0 || !w_packed || !scale || !shift || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
+    if (c0 <= 0 || (c0 % 64) || c1 < 0 || (c1 % 64) || (c1 > 0 && !src1)) return ADN_ERR_ARG;
+    if (c_out <= 0 || (c_out % 64)) return ADN_ERR_ARG;
+    if (c1 > 0 && (h1 > h || w1 > w || h1 <= 0 || w1 <= 0)) return ADN_ERR_ARG;
+    if (!aligned16(src0) || !aligned16(w_packed) || (src1 && !aligned16(src1))) return ADN_ERR_ARG;
+    if (epi == HEPI_HEAD) { if (!head_w || !head_b || !head_out || c_out != 64) return ADN_ERR_ARG; }
+    else if (!out || !aligned16(out) || (pool_out && !aligned16(pool_out))) return ADN_ERR_ARG;
+    if (pool_out && (h < 2 || w < 2)) return ADN_ERR_ARG;
+    int st = check_device();
+    if (st != ADN_OK) return st;
+
+    const int block_n = (c_out % 256 == 0) ? 256 : (c_out % 128 == 0) ? 128 : 64;
+    HaloArgs args;
+    args.c0_chunks = c0 / 64; args.c1_chunks = c1 / 64;
+    args.n_img = n; args.H = h; args.W = w;
+    args.tiles_x = (w + H_TW - 1) / H_TW; args.tiles_y = (h + H_TH - 1) / H_TH;
+    args.c_out = c_out; args.n_blocks = c_out / block_n;
+    const long long tiles = (long long)n * args.tiles_x * args.tiles_y * args.n_blocks;
+    if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
+    args.num_tiles = (int)tiles;
+    args.epi = epi;
+    args.scale = scale; args.shift = shift;
+    args.out = (__nv_bfloat16*)out; args.pool_out = (__nv_bfloat16*)pool_out;
+    args.head_w = head_w; args.head_b = head_b; args.head_out = head_out;
+
+    CUtensorMap mA0, mA1, mB;
+    st = make_act_map(&mA0, src0, n, h, w, c0, H_PITCH, H_ROWS);
+    if (st != ADN_OK) return st;
+    if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, H_PITCH, H_ROWS); else mA1 = mA0;
+    if (st != ADN_OK) return st;
+    st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), block_n);
+    if (st != ADN_OK) return st;
+
+    const int chunks = args.c0_chunks + args.c1_chunks;
+    switch (block_n) {
+        case 256: return launch_halo<256>(mA0, mA1, mB, args, chunks, stream);
+        case 128: return launch_halo<128>(mA0, mA1, mB, args, chunks, stream);
+        default: return launch_halo<64>(mA0, mA1, mB, args, chunks, stream);
+    }
+}
+
+}  // namespace adn
+
+extern "C" int adn_conv3x3_bn_relu_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
+                                        const void* w_packed, int c_out, const float* scale, const float* shift, void* out,
+                                        void* pool_out, void* stream) {
+    return adn::conv3x3_halo(src0, c0, src1, c1, h1, w1, n, h, w, w_packed, c_out, scale, shift, adn::HEPI_NHWC, out, pool_out,
+                             nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int adn_conv3x3_bn_relu_head_f32(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
+                                            const void* w_packed, int c_out, const float* scale, const float* shift,
+                                            const float* head_w, const float* head_b, float* out_f32, void* stream) {
+    if (c_out != 64) return ADN_ERR_ARG;
+    return adn::conv3x3_halo(src0, c0, src1, c1, h1, w1, n, h, w, w_packed, c_out, scale, shift, adn::HEPI_HEAD, nullptr, nullptr,
+                             head_w, head_b, out_f32, (cudaStream_t)stream);
+}

@@ -43,48 +43,48 @@ __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float*
 
 // ------------------------------------------------------------------------------------------------ first layer
 // (n,1,h,w) fp32 -> conv3x3 pad 1 (64 filters, fp32 math) -> folded BN -> ReLU -> NHWC bf16.
-// 8 lanes per pixel, 8 output channels per lane: each lane stores 16 B, a warp stores 4 pixels x 128 B contiguously.
+// HBM-bound on the 128 B/pixel it writes.  8 lanes per pixel, 8 output channels per lane: a lane keeps its 72 weights and
+// 16 BN constants in registers for the whole kernel and walks pixels with stride 32, so the inner loop is 9 broadcast loads
+// (L1 hits), 72 FMAs and one 16-byte store; a warp stores 4 pixels x 128 B = 512 contiguous bytes.
 __global__ void __launch_bounds__(256)
 conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float* __restrict__ weight,
                   const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ out) {
-    __shared__ __align__(16) float s_w[9][64];
-    __shared__ float s_scale[64], s_shift[64];
-    for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w[i % 9][i / 9] = weight[i];   // weight[c][tap]
-    if (threadIdx.x < 64) { s_scale[threadIdx.x] = scale[threadIdx.x]; s_shift[threadIdx.x] = shift[threadIdx.x]; }
-    __syncthreads();
-    const long long total = (long long)n * h * w * 8;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int cg = (int)(i & 7);
-        const long long pix = i >> 3;
+    const int cg = threadIdx.x & 7;
+    float wr[9][8], sc[8], sh[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wr[t][c] = __ldg(weight + (cg * 8 + c) * 9 + t);    // weight[c][tap]
+        sc[c] = __ldg(scale + cg * 8 + c);
+        sh[c] = __ldg(shift + cg * 8 + c);
+    }
+    const long long n_pix = (long long)n * h * w;
+    const long long stride = (long long)gridDim.x * 32;
+    for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < n_pix; pix += stride) {
         const int px = (int)(pix % w);
         const int py = (int)((pix / w) % h);
-        const long long img = pix / ((long long)w * h);
-        const float* __restrict__ xi = x + img * (long long)h * w;
+        const float* __restrict__ xc = x + pix;                  // (img, py, px) is linear in pix for a 1-channel image
         float acc[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) acc[c] = 0.f;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-            const int yy = py + ky - 1;
+            const bool yok = (unsigned)(py + ky - 1) < (unsigned)h;
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const int xx = px + kx - 1;
-                const float v = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(xi + (long long)yy * w + xx) : 0.f;
-                const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8]);
-                const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8 + 4]);
-                acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-                acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-                acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-                acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                const bool ok = yok && (unsigned)(px + kx - 1) < (unsigned)w;
+                const float v = ok ? __ldg(xc + (ky - 1) * w + (kx - 1)) : 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
             }
         }
         float y[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[c], s_scale[cg * 8 + c], s_shift[cg * 8 + c]), 0.f);
+        for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[c], sc[c], sh[c]), 0.f);
         uint4 o;
         o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
         o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-        out[i] = o;
+        __stcs(out + pix * 8 + cg, o);
     }
 }
 
@@ -221,7 +221,7 @@ extern "C" int adn_conv3x3_c1_bn_relu_bf16(const float* x, int n, int h, int w, 
                                            const float* shift, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, (uint4*)out);
+    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, (uint4*)out);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

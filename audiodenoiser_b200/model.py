@@ -166,16 +166,10 @@ class UNet(nn.Module):
         def conv(layer, src0, c0, src1, c1, h1, w1, lvl, dst, pool=None):
             p = pk[layer]
             flops = 2.0 * n * hs[lvl] * wz[lvl] * p["co"] * 9 * (c0 + c1)
-            if pool is None:
-                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
-                      src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],
-                      p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(), 0, s)
-            else:      # conv and pool are separate launches inside the C call: time them apart
-                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
-                      src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],
-                      p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(), 0, s)
-                timed(layer + ".pool", "maxpool", 0.0, 1, lib.adn_maxpool2x2_bf16, dst.data_ptr(), n, hs[lvl], wz[lvl], p["co"],
-                      pool.data_ptr(), s)
+            # the 2x2 max-pool of DownSampleLayer (model.py:31) is fused into the conv epilogue when `pool` is given
+            timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
+                  src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],
+                  p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(), pool.data_ptr() if pool is not None else 0, s)
 
         # encoder (DownSampleLayer.forward, model.py:29-32)
         p = pk["downconv1.0"]
