@@ -43,48 +43,66 @@ __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float*
 
 // ------------------------------------------------------------------------------------------------ first layer
 // (n,1,h,w) fp32 -> conv3x3 pad 1 (64 filters, fp32 math) -> folded BN -> ReLU -> NHWC bf16.
-// HBM-bound on the 128 B/pixel it writes.  8 lanes per pixel, 8 output channels per lane: a lane keeps its 72 weights and
-// 16 BN constants in registers for the whole kernel and walks pixels with stride 32, so the inner loop is 9 broadcast loads
-// (L1 hits), 72 FMAs and one 16-byte store; a warp stores 4 pixels x 128 B = 512 contiguous bytes.
+// HBM-bound on the 128 B/pixel it writes (algorithmic: 4 B in + 128 B out per pixel).  8 lanes per pixel group, 8 output
+// channels per lane, 4 consecutive pixels per lane with a sliding 3x6 input window: 18 independent loads are in flight per
+// thread, every weight vector read from shared memory feeds 4 pixels (32 FMAs per 2 LDS.128), and each store instruction of
+// a warp writes four complete 128-byte lines.
+constexpr int C1_RUN = 4;
 __global__ void __launch_bounds__(256)
 conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float* __restrict__ weight,
                   const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ out) {
-    const int cg = threadIdx.x & 7;
-    float wr[9][8], sc[8], sh[8];
+    __shared__ __align__(16) float s_w[9][64];
+    for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w[i % 9][i / 9] = weight[i];   // weight[c][tap]
+    const int cg = threadIdx.x & 7, grp = threadIdx.x >> 3;
+    float sc[8], sh[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < 8; ++c) { sc[c] = __ldg(scale + cg * 8 + c); sh[c] = __ldg(shift + cg * 8 + c); }
+    __syncthreads();
+    const int n_rows = n * h;
+    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const int py = row % h;
+        const float* __restrict__ xr = x + (long long)row * w;
+        const bool rok[3] = {py > 0, true, py + 1 < h};
+        uint4* __restrict__ orow = out + (long long)row * w * 8 + cg;
+        for (int px0 = grp * C1_RUN; px0 < w; px0 += 32 * C1_RUN) {
+            float v[3][C1_RUN + 2];
 #pragma unroll
-        for (int t = 0; t < 9; ++t) wr[t][c] = __ldg(weight + (cg * 8 + c) * 9 + t);    // weight[c][tap]
-        sc[c] = __ldg(scale + cg * 8 + c);
-        sh[c] = __ldg(shift + cg * 8 + c);
-    }
-    const long long n_pix = (long long)n * h * w;
-    const long long stride = (long long)gridDim.x * 32;
-    for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < n_pix; pix += stride) {
-        const int px = (int)(pix % w);
-        const int py = (int)((pix / w) % h);
-        const float* __restrict__ xc = x + pix;                  // (img, py, px) is linear in pix for a 1-channel image
-        float acc[8];
+            for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+                for (int i = 0; i < C1_RUN + 2; ++i) {
+                    const int xx = px0 + i - 1;
+                    v[ky][i] = (rok[ky] && xx >= 0 && xx < w) ? __ldg(xr + (ky - 1) * w + xx) : 0.f;
+                }
+            float acc[C1_RUN][8];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const bool yok = (unsigned)(py + ky - 1) < (unsigned)h;
+            for (int r = 0; r < C1_RUN; ++r)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const bool ok = yok && (unsigned)(px + kx - 1) < (unsigned)w;
-                const float v = ok ? __ldg(xc + (ky - 1) * w + (kx - 1)) : 0.f;
+                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[c] = fmaf(v, wr[ky * 3 + kx][c], acc[c]);
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8 + 4]);
+                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int r = 0; r < C1_RUN; ++r)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(v[ky][r + kx], wv[c], acc[r][c]);
+                }
+#pragma unroll
+            for (int r = 0; r < C1_RUN; ++r) {
+                if (px0 + r < w) {
+                    float y[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[r][c], sc[c], sh[c]), 0.f);
+                    uint4 o;
+                    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+                    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+                    __stcs(orow + (long long)(px0 + r) * 8, o);
+                }
             }
         }
-        float y[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[c], sc[c], sh[c]), 0.f);
-        uint4 o;
-        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-        o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-        __stcs(out + pix * 8 + cg, o);
     }
 }
 

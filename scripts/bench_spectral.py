@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""STFT / iSTFT kernel throughput at BASELINE config 2 (4 096-clip dataset-creation batch) and at the bench batch.
+Prints GB/s of algorithmic bytes against the measured HBM copy peak.  usage: python scripts/bench_spectral.py [reps]"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from audiodenoiser_b200 import spectral  # noqa: E402
+
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+dev = torch.device("cuda", 0)
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+out = {}
+for name, n, length, center in (("c2_R_4096x24000", 4096, 24000, True), ("c2_train_4096x16000", 4096, 16000, False),
+                                ("B_64x132300", 64, 132300, True), ("B_512x132300", 512, 132300, True)):
+    g = torch.Generator(device=dev).manual_seed(0)
+    x = torch.rand((n, length), device=dev, generator=g) * 2 - 1
+    t = spectral.num_frames(length, center)
+    mag = torch.empty((n, 257, t), device=dev)
+    ms = timeit(lambda: spectral.stft_mag_batched(x, center, out=mag))
+    b = n * (4 * length + 4 * 257 * t)
+    out["stft_" + name] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
+    if center:
+        audio = torch.empty((n, 128 * (t - 1)), device=dev)
+        ms = timeit(lambda: spectral.istft_batched(mag, None, seed=1, out=audio))
+        b = n * (4 * 257 * t + 4 * 128 * (t - 1))
+        out["istft_rand_" + name] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
+        if n * 257 * t * 8 < 8e9:
+            ph = torch.polar(torch.ones_like(mag), torch.rand_like(mag) * 6.2831853)
+            ms = timeit(lambda: spectral.istft_batched(mag, ph, out=audio))
+            b = n * (12 * 257 * t + 4 * 128 * (t - 1))
+            out["istft_phasor_" + name] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
+            del ph
+    del x, mag
+for k, v in out.items():
+    print(k, v)
