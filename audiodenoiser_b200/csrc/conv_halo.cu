@@ -28,6 +28,8 @@ constexpr int H_A_STAGE = H_ROWS * H_PITCH * 128;  // 36 864 B
 constexpr int H_THREADS = 224;
 constexpr int H_EPI_THREADS = 128;
 constexpr int H_MAX_A = 8, H_MAX_B = 16;
+constexpr int H_OUT_STAGE = 128 * 128;             // one 128-pixel x 64-channel bf16 output tile
+constexpr int H_POOL_STAGE = 32 * 128;             // its 2x2-pooled counterpart
 
 enum { HEPI_NHWC = 0, HEPI_HEAD = 2 };
 
@@ -38,6 +40,7 @@ struct HaloArgs {
     int c_out, n_blocks, num_tiles;
     int epi;
     int a_stages, b_slots, b_resident;
+    int tma_store;                 // epilogue stages bf16 tiles in smem and stores them with TMA (when the smem budget allows)
     const float* scale;
     const float* shift;
     __nv_bfloat16* out;
@@ -50,7 +53,8 @@ struct HaloArgs {
 template <int BLOCK_N, bool B_RESIDENT>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                    const __grid_constant__ CUtensorMap tmB, const HaloArgs a) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmPool, const HaloArgs a) {
     constexpr int B_BLOCK = BLOCK_N * 128;                         // bytes of one (tap, chunk) weight block
     constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_dyn[];
@@ -59,7 +63,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)a.a_stages * H_A_STAGE;
-    const uint32_t aux_off = (uint32_t)a.a_stages * H_A_STAGE + (uint32_t)a.b_slots * B_BLOCK;
+    // epilogue staging (TMA-store mode): 2 x [128 px][64 ch] bf16 (+ 2 x [32 pooled px][64 ch]), SWIZZLE_128B, 1024-B aligned
+    const uint32_t stage_off = (uint32_t)a.a_stages * H_A_STAGE + (uint32_t)a.b_slots * B_BLOCK;
+    const uint32_t stage_bytes = a.tma_store ? (2u * H_OUT_STAGE + (a.pool_out ? 2u * H_POOL_STAGE : 0u)) : 0u;
+    const uint32_t aux_off = stage_off + stage_bytes;
     float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);     // [c_out] all output channels, loaded once per CTA
     float* s_shift = s_scale + a.c_out;
     float* s_head = s_shift + a.c_out;
@@ -80,6 +87,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
         tma_prefetch_desc(&tmB);
+        if (a.tma_store) { tma_prefetch_desc(&tmOut); if (a.pool_out) tma_prefetch_desc(&tmPool); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < H_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
@@ -212,6 +220,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         named_bar_sync(1, H_EPI_THREADS);
         const int Hp = a.H >> 1, Wp = a.W >> 1;
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t store_groups = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const int n_blk = tile % a.n_blocks;
             const int m = tile / a.n_blocks;
@@ -249,7 +258,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                         pk[i] = *reinterpret_cast<uint32_t*>(&p);
                     }
                     const int n = n_blk * BLOCK_N + c0;
-                    if (valid) {
+                    const bool first_half = (c0 & 32) == 0;
+                    uint32_t o_stage = 0, p_stage = 0;
+                    if (a.tma_store) {                                // warp-uniform
+                        const uint32_t buf = store_groups & 1u;
+                        o_stage = smem_base + stage_off + buf * H_OUT_STAGE;
+                        p_stage = smem_base + stage_off + 2u * H_OUT_STAGE + buf * H_POOL_STAGE;
+                        if (first_half) {                             // this buffer's previous TMA store must have read it
+                            if (et == 0) bulk_wait_read<1>();
+                            named_bar_sync(1, H_EPI_THREADS);
+                        }
+                        const uint32_t rbase = o_stage + (uint32_t)row * 128u;
+                        const uint32_t cbase = first_half ? 0u : 4u;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            st_shared_v4(rbase + (((cbase + i) ^ ((uint32_t)row & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                    } else if (valid) {
                         uint4* d4 = reinterpret_cast<uint4*>(a.out + (((long long)img * a.H + y) * a.W + x) * a.c_out + n);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
@@ -267,11 +291,31 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                             m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&o8));
                             pk[i] = *reinterpret_cast<uint32_t*>(&m0);
                         }
-                        if (pool_writer) {
+                        if (a.tma_store) {
+                            if (!(lx & 1) && !(ly & 1)) {
+                                const uint32_t pr = (uint32_t)((ly >> 1) * 4 + (lx >> 1));
+                                const uint32_t rbase = p_stage + pr * 128u;
+                                const uint32_t cbase = first_half ? 0u : 4u;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    st_shared_v4(rbase + (((cbase + i) ^ (pr & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                            }
+                        } else if (pool_writer) {
                             uint4* d4 = reinterpret_cast<uint4*>(a.pool_out + (((long long)img * Hp + (y >> 1)) * Wp + (x >> 1)) * a.c_out + n);
 #pragma unroll
                             for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
                         }
+                    }
+                    if (a.tma_store && !first_half) {                 // a 64-channel group is staged: hand it to the TMA engine
+                        fence_proxy_async();
+                        named_bar_sync(1, H_EPI_THREADS);
+                        if (et == 0) {
+                            const int ch0 = n_blk * BLOCK_N + (c0 - 32);
+                            tma_store_4d(&tmOut, o_stage, ch0, tx * H_TW, ty * H_TH, img);
+                            if (a.pool_out) tma_store_4d(&tmPool, p_stage, ch0, tx * (H_TW / 2), ty * (H_TH / 2), img);
+                            bulk_commit();
+                        }
+                        ++store_groups;
                     }
                 }
             }
@@ -282,6 +326,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             if (lane == 0) mbar_arrive(tempty(acc));                 // 4 arrivals (one per epilogue warp) free the accumulator
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (a.tma_store && et == 0) bulk_wait<0>();                    // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
@@ -292,36 +337,43 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
 // ------------------------------------------------------------------------------------------------ host side
 template <int BLOCK_N>
-static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, HaloArgs& args, int chunks,
-                       cudaStream_t stream) {
+static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const CUtensorMap& mOut,
+                       const CUtensorMap& mPool, HaloArgs& args, int chunks, cudaStream_t stream) {
     constexpr int B_BLOCK = BLOCK_N * 128;
     const int AUX = (2 * args.c_out + 64) * 4 + (2 * H_MAX_A + 2 * H_MAX_B + 5) * 8 + 16;
     constexpr int MAX_DYN = 232448;
     const int budget = MAX_DYN - 1024 - AUX;
     const int total_b = 9 * chunks * B_BLOCK;
+    // TMA-store staging is worth its shared memory only where it does not starve the operand rings
+    const int staging = (args.epi == HEPI_NHWC) ? 2 * H_OUT_STAGE + (args.pool_out ? 2 * H_POOL_STAGE : 0) : 0;
+    args.tma_store = 0;
     if (args.n_blocks == 1 && total_b + 2 * H_A_STAGE <= budget) {
         args.b_resident = 1;
         args.b_slots = 9 * chunks;
-        int st = (budget - total_b) / H_A_STAGE;
+        int avail = budget - total_b;
+        if (staging && avail - staging >= 3 * H_A_STAGE) { args.tma_store = 1; avail -= staging; }
+        const int st = avail / H_A_STAGE;
         args.a_stages = st > H_MAX_A ? H_MAX_A : st;
     } else {
         args.b_resident = 0;
         args.a_stages = (BLOCK_N >= 256) ? 2 : 3;
-        int sl = (budget - args.a_stages * H_A_STAGE) / B_BLOCK;
+        int avail = budget - args.a_stages * H_A_STAGE;
+        if (staging && (avail - staging) / B_BLOCK >= 4) { args.tma_store = 1; avail -= staging; }
+        const int sl = avail / B_BLOCK;
         args.b_slots = sl > H_MAX_B ? H_MAX_B : sl;
         if (args.b_slots < 2) return ADN_ERR_ARG;
     }
-    const int smem = 1024 + args.a_stages * H_A_STAGE + args.b_slots * B_BLOCK + AUX;
+    const int smem = 1024 + args.a_stages * H_A_STAGE + args.b_slots * B_BLOCK + (args.tma_store ? staging : 0) + AUX;
     const int sms = num_sms();
     const int grid = args.num_tiles < sms ? args.num_tiles : sms;
     if (args.b_resident) {
         static unsigned char smem_set[64] = {0};
         ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true>, MAX_DYN, smem_set));
-        conv3x3_halo_kernel<BLOCK_N, true><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, args);
+        conv3x3_halo_kernel<BLOCK_N, true><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
     } else {
         static unsigned char smem_set[64] = {0};
         ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false>, MAX_DYN, smem_set));
-        conv3x3_halo_kernel<BLOCK_N, false><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, args);
+        conv3x3_halo_kernel<BLOCK_N, false><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
     }
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -363,11 +415,20 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), block_n);
     if (st != ADN_OK) return st;
 
+    // output maps for the TMA-store epilogue: box {64 ch, 8 px, 16 rows} of the NHWC output, {64, 4, 8} of the pooled one
+    CUtensorMap mOut = mA0, mPool = mA0;
+    if (epi == HEPI_NHWC) {
+        st = make_act_map(&mOut, out, n, h, w, c_out, H_TW, H_TH);
+        if (st != ADN_OK) return st;
+        if (pool_out) st = make_act_map(&mPool, pool_out, n, h / 2, w / 2, c_out, H_TW / 2, H_TH / 2);
+        if (st != ADN_OK) return st;
+    }
+
     const int chunks = args.c0_chunks + args.c1_chunks;
     switch (block_n) {
-        case 256: return launch_halo<256>(mA0, mA1, mB, args, chunks, stream);
-        case 128: return launch_halo<128>(mA0, mA1, mB, args, chunks, stream);
-        default: return launch_halo<64>(mA0, mA1, mB, args, chunks, stream);
+        case 256: return launch_halo<256>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        case 128: return launch_halo<128>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        default: return launch_halo<64>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
     }
 }
 

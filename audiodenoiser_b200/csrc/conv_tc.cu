@@ -1,89 +1,77 @@
-// conv_tc.cu -- tap-streaming tcgen05/TMEM implicit-GEMM kernel for sm_100a.  In the product it runs the reference UNet's
-// ConvTranspose2d 2x2/2 (code/model.py:38,43: one tap, GEMM N = 4*Cout with a pixel-shuffle store); the 3x3 convolutions
-// moved to conv_halo.cu, which keeps the halo tile resident in shared memory instead of re-fetching it per tap.
+// conv_tc.cu -- ConvTranspose2d(k=2, s=2) + bias of the reference UNet (code/model.py:38,43) as a persistent, warp-specialised
+// tcgen05/TMEM GEMM with a pixel-shuffle TMA-store epilogue, for sm_100a.
 //
-//   GEMM view     D[M = n*h*w pixels, N = c_out] = A[M, K] * B[N, K]^T,  K = taps * c_in (taps = 9 or 1), bf16 x bf16 -> fp32
-//   A operand     never materialised: for every (tap, 64-channel chunk) one 4-D TMA box {64 ch, TW, TH, 1 image} of the
-//                 NHWC activation, shifted by the tap offset; out-of-bounds rows/columns arrive as zeros, which is the
-//                 conv's zero padding AND the F.pad of the up-sampled tensor (model.py:44-47).  The K range may be split
-//                 over two tensors (skip, up) -- torch.cat([x2, x1]) of model.py:49 is never built.
-//                 TH*TW = 128 pixels = the 128 TMEM lanes of one accumulator; the box lands as a K-major SWIZZLE_128B
-//                 tile, exactly what the UMMA descriptor expects.
-//   B operand     packed weights [N][K] bf16 (K-major), 2-D TMA box {64, BLOCK_N}.
-//   roles         warp 0: TMA producer (1 elected lane) - warp 1: tcgen05.mma issuer (1 lane) - warps 2..5: epilogue
-//                 (tcgen05.ld -> fp32 BN scale/shift -> ReLU -> bf16 -> 16-byte global stores).  smem ring of STAGES
-//                 {A,B} buffers with full/empty mbarriers; two TMEM accumulators so the epilogue of tile i overlaps the
-//                 MMAs of tile i+1.
-//   epilogue      + bias, bf16, pixel-shuffle store: GEMM column n = q*Cout + co of input pixel (y,x) -> output (2y+dy, 2x+dx, co).
+//   GEMM view     D[M = n*h*w input pixels, N = 4*Cout] = A[M, K = Cin] * B[N, K]^T   (bf16 x bf16 -> fp32);
+//                 column n = q*Cout + co with q = dy*2 + dx is output pixel (2y+dy, 2x+dx), channel co.
+//   A operand     per 64-channel chunk one 4-D TMA box {64 ch, TW, TH, 1 image} of the NHWC input (TH*TW = 128 pixels = the 128
+//                 TMEM lanes), landing as a K-major SWIZZLE_128B tile.
+//   B operand     packed weights [q][Cout][Cin] bf16 (K-major), 2-D TMA box {64, 256}.
+//   roles         warp 0: TMA producer - warp 1: tcgen05.mma issuer (warp-uniform loop, elect.sync around the issue) -
+//                 warps 2..5: epilogue.  Ring of STAGES {A,B} buffers with full/empty mbarriers; two TMEM accumulators so the
+//                 epilogue of tile i overlaps the MMAs of tile i+1.
+//   epilogue      tcgen05.ld -> + bias -> bf16 -> a [128 px][64 ch] SWIZZLE_128B staging tile in smem -> ONE TMA store per
+//                 (quadrant, 64-channel group) through a tensor map of the strided output view {co, x (stride 2), y (stride 2), n}
+//                 based at (dy, dx): the pixel shuffle costs no scattered 16-byte stores (the first version of this kernel
+//                 spent ~2x its HBM time in the LSU), and out-of-image rows / columns are clipped by the TMA engine.
 #include "tc_common.cuh"
 
 namespace adn {
 
-// ------------------------------------------------------------------------------------------------ kernel
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                 // bf16 elements = one 128-byte swizzle row
+constexpr int T_BLOCK_N = 256;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int B_STAGE_BYTES = T_BLOCK_N * BLOCK_K * 2;
+constexpr int T_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 48 KB
+constexpr int T_STAGES = 3;
+constexpr int T_OUT_STAGE = 128 * 128;                             // [128 px][64 ch] bf16
+constexpr int T_MAX_COUT = 512;
 constexpr int CONV_THREADS = 192;
 constexpr int EPI_THREADS = 128;
+constexpr int T_AUX_BYTES = T_MAX_COUT * 4 + (2 * T_STAGES + 4) * 8 + 16;
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + 2 * T_OUT_STAGE + T_AUX_BYTES + 1024;
 
-
-struct ConvArgs {
-    int c0_chunks, c1_chunks;      // 64-channel chunks taken from source 0 / source 1
-    int taps;                      // 9 (3x3, pad 1) or 1
-    int n_img, H, W;               // GEMM rows = n_img*H*W pixels of the A tensors' grid
+struct ConvTArgs {
+    int k_chunks;                  // Cin / 64
+    int n_img, H, W;               // input pixel grid
     int tiles_x, tiles_y, tw_log2; // pixel tile = TH x TW, TW = 1 << tw_log2, TH = 128 >> tw_log2
-    int n_total;                   // GEMM N (c_out, or 4*c_out for the transposed conv)
-    int c_out;                     // channels of the output tensor
-    int n_blocks;                  // n_total / BLOCK_N
-    int num_tiles;                 // n_img*tiles_y*tiles_x*n_blocks
-    const float* shift;            // bias[c_out]
-    __nv_bfloat16* out;
+    int c_out, n_blocks, num_tiles;
+    const float* bias;             // [c_out]
 };
 
-template <int BLOCK_N>
-struct ConvCfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
-    static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;     // 128 / 256 / 512: powers of two
-    static constexpr int AUX_BYTES = 2 * BLOCK_N * 4 + 64 * 4 + (2 * STAGES + 4) * 8 + 16;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;  // +1024: manual 1024-byte alignment
-};
-
-template <int BLOCK_N>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                 const __grid_constant__ CUtensorMap tmB, const ConvArgs a) {
-    using Cfg = ConvCfg<BLOCK_N>;
-    constexpr int STAGES = Cfg::STAGES;
+convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                  const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3, const ConvTArgs a) {
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
-    // carve-up: [STAGES x {A, B}] [scale BLOCK_N] [shift BLOCK_N] [head_w 64] [full STAGES] [empty STAGES] [tfull 2] [tempty 2] [tmem ptr]
-    float* s_scale = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES);
-    float* s_shift = s_scale + BLOCK_N;
-    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES + (2 * BLOCK_N + 64) * 4;
+    // carve-up: [STAGES x {A, B}] [2 x output staging] [bias] [full STAGES] [empty STAGES] [tfull 2] [tempty 2] [tmem ptr]
+    const uint32_t out_stage_base = smem_base + T_STAGES * T_STAGE_BYTES;
+    constexpr uint32_t AUX_OFF = T_STAGES * T_STAGE_BYTES + 2 * T_OUT_STAGE;
+    float* s_bias = reinterpret_cast<float*>(smem_gen + AUX_OFF);
+    const uint32_t bar_base = smem_base + AUX_OFF + T_MAX_COUT * 4;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + (2 * BLOCK_N + 64) * 4 + (2 * STAGES + 4) * 8);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (T_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * T_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * T_STAGES + 2 + s); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + AUX_OFF + T_MAX_COUT * 4 + (2 * T_STAGES + 4) * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA0);
-        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO0); tma_prefetch_desc(&tmO1); tma_prefetch_desc(&tmO2); tma_prefetch_desc(&tmO3);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < T_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_THREADS / 32); }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+        tmem_alloc(smem_u32(tmem_ptr_smem), 2 * T_BLOCK_N);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -91,8 +79,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int chunks = a.c0_chunks + a.c1_chunks;
-    const int num_kb = a.taps * chunks;
     const int TW = 1 << a.tw_log2, TH = BLOCK_M >> a.tw_log2;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
 
@@ -106,36 +92,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                 const int img = m / tiles_per_img;
                 const int rem = m - img * tiles_per_img;
                 const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-                const int x0 = tx * TW, y0 = ty * TH;
-                for (int tap = 0; tap < a.taps; ++tap) {
-                    const int dy = (a.taps == 9) ? tap / 3 - 1 : 0;
-                    const int dx = (a.taps == 9) ? tap % 3 - 1 : 0;
-                    for (int ch = 0; ch < chunks; ++ch) {
-                        mbar_wait(empty_bar(stage), phase ^ 1u);
-                        const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
-                        const uint32_t sb = sa + A_STAGE_BYTES;
-                        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-                        if (ch < a.c0_chunks) tma_load_4d(sa, &tmA0, full_bar(stage), ch * BLOCK_K, x0 + dx, y0 + dy, img);
-                        else tma_load_4d(sa, &tmA1, full_bar(stage), (ch - a.c0_chunks) * BLOCK_K, x0 + dx, y0 + dy, img);
-                        tma_load_2d(sb, &tmB, full_bar(stage), (tap * chunks + ch) * BLOCK_K, n_blk * BLOCK_N);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                    }
+                for (int ch = 0; ch < a.k_chunks; ++ch) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * T_STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), T_STAGE_BYTES);
+                    tma_load_4d(sa, &tmA, full_bar(stage), ch * BLOCK_K, tx * TW, ty * TH, img);
+                    tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), ch * BLOCK_K, n_blk * T_BLOCK_N);
+                    if (++stage == T_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer (whole warp, one elected lane issues)
-        constexpr uint32_t idesc = make_idesc(BLOCK_N);
+        constexpr uint32_t idesc = make_idesc(T_BLOCK_N);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * T_BLOCK_N);
+            for (int kb = 0; kb < a.k_chunks; ++kb) {
                 mbar_wait(full_bar(stage), phase);               // TMA bytes have landed
                 tc_fence_after();
-                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                const uint32_t sa = smem_base + stage * T_STAGE_BYTES;
                 const uint64_t da = make_sw128_desc(sa);
                 const uint64_t db = make_sw128_desc(sa + A_STAGE_BYTES);
                 if (elect_one()) {
@@ -145,7 +124,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
                     umma_commit(empty_bar(stage));               // frees the smem slot when these MMAs retire
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                if (++stage == T_STAGES) { stage = 0; phase ^= 1u; }
             }
             if (elect_one()) umma_commit(tfull_bar(acc));        // accumulator complete -> epilogue
             __syncwarp();
@@ -156,109 +135,125 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;                            // accumulator row = input pixel within the tile
         const int et = threadIdx.x - 64;                             // 0..127
-        const int lx = row & (TW - 1), ly = row >> a.tw_log2;
-        float* s_bias = s_scale;                                     // [c_out] <= 2*BLOCK_N floats, loaded once per CTA
-        for (int c = et; c < a.c_out; c += EPI_THREADS) s_bias[c] = a.shift[c];
+        for (int c = et; c < a.c_out; c += EPI_THREADS) s_bias[c] = a.bias[c];
         named_bar_sync(1, EPI_THREADS);
         int acc = 0; uint32_t acc_phase = 0;
+        uint32_t store_groups = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
             const int n_blk = tile % a.n_blocks;
             const int m = tile / a.n_blocks;
             const int img = m / tiles_per_img;
             const int rem = m - img * tiles_per_img;
             const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
-            const int x = tx * TW + lx, y = ty * TH + ly;
-            const bool valid = (x < a.W) && (y < a.H);
 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * T_BLOCK_N);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + (uint32_t)c0, r);
-                tmem_ld_wait();
-                const int n = n_blk * BLOCK_N + c0;                  // first GEMM column of this 32-wide chunk
-                const int q = n / a.c_out, co = n - q * a.c_out;     // q = dy*2 + dx ; a chunk never straddles a quadrant
-                const float* bias = s_bias + co;
-                if (valid) {
-                    // pixel-shuffle store: input pixel (y, x) -> output pixel (2y + dy, 2x + dx), channels co .. co+31
-                    const long long pix = ((long long)img * (2 * a.H) + (2 * y + (q >> 1))) * (2 * a.W) + (2 * x + (q & 1));
-                    uint4* d4 = reinterpret_cast<uint4*>(a.out + pix * a.c_out + co);
+            for (int g = 0; g < T_BLOCK_N / 64; ++g) {               // one 64-column group = one (quadrant, 64-channel) store
+                const int n = n_blk * T_BLOCK_N + g * 64;
+                const int q = n / a.c_out, co = n - q * a.c_out;     // a group never straddles a quadrant (c_out % 64 == 0)
+                const uint32_t o_stage = out_stage_base + (store_groups & 1u) * T_OUT_STAGE;
+                if (et == 0) bulk_wait_read<1>();                    // the store that last used this buffer has read it
+                named_bar_sync(1, EPI_THREADS);
+                const uint32_t rbase = o_stage + (uint32_t)row * 128u;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + (uint32_t)(g * 64 + half * 32), r);
+                    tmem_ld_wait();
+                    const float* bias = s_bias + co + half * 32;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        uint4 o;
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 0]) + bias[8 * i + 0], __uint_as_float(r[8 * i + 1]) + bias[8 * i + 1]);
-                        __nv_bfloat162 p1 = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2]) + bias[8 * i + 2], __uint_as_float(r[8 * i + 3]) + bias[8 * i + 3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 4]) + bias[8 * i + 4], __uint_as_float(r[8 * i + 5]) + bias[8 * i + 5]);
-                        __nv_bfloat162 p3 = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 6]) + bias[8 * i + 6], __uint_as_float(r[8 * i + 7]) + bias[8 * i + 7]);
-                        o.x = *reinterpret_cast<uint32_t*>(&p0); o.y = *reinterpret_cast<uint32_t*>(&p1);
-                        o.z = *reinterpret_cast<uint32_t*>(&p2); o.w = *reinterpret_cast<uint32_t*>(&p3);
-                        d4[i] = o;
+                        uint32_t w[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * j]) + bias[8 * i + 2 * j],
+                                                                      __uint_as_float(r[8 * i + 2 * j + 1]) + bias[8 * i + 2 * j + 1]);
+                            w[j] = *reinterpret_cast<uint32_t*>(&p);
+                        }
+                        st_shared_v4(rbase + ((((uint32_t)(half * 4 + i)) ^ ((uint32_t)row & 7u)) << 4), w[0], w[1], w[2], w[3]);
                     }
                 }
+                fence_proxy_async();
+                named_bar_sync(1, EPI_THREADS);
+                if (et == 0) {
+                    const CUtensorMap* mo = (q == 0) ? &tmO0 : (q == 1) ? &tmO1 : (q == 2) ? &tmO2 : &tmO3;
+                    tma_store_4d(mo, o_stage, co, tx * TW, ty * TH, img);
+                    bulk_commit();
+                }
+                ++store_groups;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));             // 4 arrivals (one per epilogue warp) free the accumulator
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+        if (et == 0) bulk_wait<0>();                                 // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * T_BLOCK_N);
 }
 
-template <int BLOCK_N>
-static int launch_cfg(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const ConvArgs& args, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N>;
-    auto kern = conv_gemm_kernel<BLOCK_N>;
-    static unsigned char smem_set[64] = {0};
-    ADN_CUDA_TRY(ensure_dyn_smem(kern, Cfg::SMEM_BYTES, smem_set));
-    const int sms = num_sms();
-    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
-    kern<<<grid, CONV_THREADS, Cfg::SMEM_BYTES, stream>>>(mA0, mA1, mB, args);
-    ADN_LAUNCH_CHECK();
-    return ADN_OK;
+// ------------------------------------------------------------------------------------------------ host side
+// strided view of the (n, 2h, 2w, c_out) output for quadrant (dy, dx): element (co, x, y, img) = out[img][2y+dy][2x+dx][co]
+static int make_shuffle_map(CUtensorMap* map, void* out, int n, int h, int w, int c_out, int dy, int dx, int tw, int th) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) return ADN_ERR_DRIVER;
+    char* base = static_cast<char*>(out) + ((size_t)dy * (2 * w) + dx) * c_out * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c_out, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)2 * c_out * 2, (cuuint64_t)2 * (2 * w) * c_out * 2, (cuuint64_t)(2 * h) * (2 * w) * c_out * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
 }
 
-// common driver: A sources on an (n,h,w) pixel grid; src1 may have a smaller spatial extent (h1,w1)
-// ConvTranspose2d(k=2, s=2) as a GEMM over the input pixel grid: M = n*h*w, K = c_in, N = 4*c_out (q-major).
 static int convt_gemm(const void* src, int c_in, int n, int h, int w, const void* w_packed, int c_out, const float* bias, void* out,
                       cudaStream_t stream) {
     if (!src || !w_packed || !bias || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
-    if (c_in <= 0 || (c_in % 64) || c_out <= 0 || (c_out % 64)) return ADN_ERR_ARG;
+    if (c_in <= 0 || (c_in % 64) || c_out <= 0 || (c_out % 64) || c_out > T_MAX_COUT) return ADN_ERR_ARG;
     if (!aligned16(src) || !aligned16(w_packed) || !aligned16(out)) return ADN_ERR_ARG;
     int st = check_device();
     if (st != ADN_OK) return st;
-    const int n_total = 4 * c_out;
+    const int n_total = 4 * c_out;                            // always a multiple of 256
 
     // pixel tile: 8x16 or 16x8 (TH x TW), whichever wastes fewer padded pixels
     auto padded = [&](int th, int tw) { return (long long)((h + th - 1) / th) * th * ((w + tw - 1) / tw) * tw; };
     const int tw_log2 = padded(8, 16) <= padded(16, 8) ? 4 : 3;
     const int tw = 1 << tw_log2, th = BLOCK_M >> tw_log2;
 
-    const int block_n = 256;                                  // 4*c_out is always a multiple of 256
-    if (c_out > 2 * block_n) return ADN_ERR_ARG;              // bias staging area holds 2*BLOCK_N floats
-    ConvArgs args;
-    args.c0_chunks = c_in / 64; args.c1_chunks = 0; args.taps = 1;
+    ConvTArgs args;
+    args.k_chunks = c_in / 64;
     args.n_img = n; args.H = h; args.W = w;
     args.tiles_x = (w + tw - 1) / tw; args.tiles_y = (h + th - 1) / th; args.tw_log2 = tw_log2;
-    args.n_total = n_total; args.c_out = c_out; args.n_blocks = n_total / block_n;
+    args.c_out = c_out; args.n_blocks = n_total / T_BLOCK_N;
     const long long tiles = (long long)n * args.tiles_x * args.tiles_y * args.n_blocks;
     if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
     args.num_tiles = (int)tiles;
-    args.shift = bias;
-    args.out = (__nv_bfloat16*)out;
+    args.bias = bias;
 
-    CUtensorMap mA0, mB;
-    st = make_act_map(&mA0, src, n, h, w, c_in, tw, th);
+    CUtensorMap mA, mB, mO[4];
+    st = make_act_map(&mA, src, n, h, w, c_in, tw, th);
     if (st != ADN_OK) return st;
-    st = make_weight_map(&mB, w_packed, n_total, c_in, block_n);
+    st = make_weight_map(&mB, w_packed, n_total, c_in, T_BLOCK_N);
     if (st != ADN_OK) return st;
-    return launch_cfg<256>(mA0, mA0, mB, args, stream);
+    for (int q = 0; q < 4; ++q) {
+        st = make_shuffle_map(&mO[q], out, n, h, w, c_out, q >> 1, q & 1, tw, th);
+        if (st != ADN_OK) return st;
+    }
+
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(convt_gemm_kernel, T_SMEM_BYTES, smem_set));
+    const int sms = num_sms();
+    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    convt_gemm_kernel<<<grid, CONV_THREADS, T_SMEM_BYTES, stream>>>(mA, mB, mO[0], mO[1], mO[2], mO[3], args);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
 }
 
 }  // namespace adn

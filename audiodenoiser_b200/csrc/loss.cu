@@ -1,0 +1,234 @@
+// loss.cu -- CombinedPerceptualLoss forward of the reference (code/loss.py:6-95) as three small sm_100a kernels.
+//
+//   loss.py:14-20 / 46-52   mean over the frequency axis -> per-sample time envelope (B, T)         \  loss_envelope_kernel
+//   loss.py:76,86           nn.L1Loss(pred, target): mean |pred - target| over every element        /  (one pass over the inputs)
+//   loss.py:22-35           three rectangular-window STFTs of the envelope (n_fft 63/32/16, hop 16/8/4, center=True with
+//                           zero padding, onesided), |.|, L1, averaged over the scales               \  loss_spectral_kernel
+//   loss.py:40-42,60-69     torchaudio MelSpectrogram(sr 8000, n_fft 63, hop 16, n_mels 64): periodic Hann(63), reflect
+//                           padding, power spectrum, HTK filterbank (32 x 64, no norm), L1           /  (one CTA per sample)
+//   loss.py:88-95           total = 0.4 stft + 0.4 mel + 0.2 l1                                        loss_finalize_kernel
+//
+// The envelopes are tiny (B x T), so the transforms are direct DFTs from shared memory with an exact-angle twiddle table
+// instead of an FFT: a few hundred thousand MACs per sample.  All reductions are two-stage and ordered (no atomics), so the
+// four scalars are bit-reproducible run to run.  HBM-bound on the single read of pred and target (8 bytes per element).
+#include "adn_common.cuh"
+
+namespace adn {
+
+constexpr int LOSS_MAX_T = 8192;
+constexpr int ENV_TX = 32, ENV_FY = 8;
+constexpr int MEL_NFFT = 63, MEL_BINS = 32, MEL_N = 64, MEL_HOP = 16;
+
+// ------------------------------------------------------------------------------------------------ envelope + L1
+// grid (ceil(T/32), B); block (32, 8): lane x owns time column t, the 8 y-slices stride the frequency axis.
+__global__ void __launch_bounds__(ENV_TX * ENV_FY)
+loss_envelope_kernel(const float* __restrict__ pred, const float* __restrict__ target, int F, int T,
+                     float* __restrict__ env, double* __restrict__ l1_partial) {
+    __shared__ float sp[ENV_FY][ENV_TX], stg[ENV_FY][ENV_TX];
+    __shared__ double sl[ENV_FY];
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * ENV_TX + threadIdx.x;
+    const size_t base = (size_t)b * F * T;
+    float ap = 0.f, at = 0.f, al = 0.f;
+    if (t < T) {
+        for (int f = threadIdx.y; f < F; f += ENV_FY) {
+            const float p = __ldcs(pred + base + (size_t)f * T + t), g = __ldcs(target + base + (size_t)f * T + t);
+            ap += p; at += g; al += fabsf(p - g);
+        }
+    }
+    sp[threadIdx.y][threadIdx.x] = ap;
+    stg[threadIdx.y][threadIdx.x] = at;
+    double l = (double)al;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (threadIdx.x == 0) sl[threadIdx.y] = l;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        if (t < T) {
+            float a = 0.f, c = 0.f;
+#pragma unroll
+            for (int y = 0; y < ENV_FY; ++y) { a += sp[y][threadIdx.x]; c += stg[y][threadIdx.x]; }
+            env[((size_t)b * 2 + 0) * T + t] = a / (float)F;
+            env[((size_t)b * 2 + 1) * T + t] = c / (float)F;
+        }
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int y = 0; y < ENV_FY; ++y) s += sl[y];
+            l1_partial[(size_t)b * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ spectral terms
+__device__ __forceinline__ double block_sum(double v, double* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    return s;       // valid in thread 0
+}
+
+// one CTA per sample; sums[b] = { sum|dmag| scale 63, scale 32, scale 16, sum|dmel| }
+__global__ void __launch_bounds__(256)
+loss_spectral_kernel(const float* __restrict__ env, int T, const float* __restrict__ mel_fb, double* __restrict__ sums) {
+    extern __shared__ float smem[];
+    float* xp = smem;                       // [T]
+    float* xt = xp + T;                     // [T]
+    float* tw_c = xt + T;                   // [64] cos(2 pi m / n)
+    float* tw_s = tw_c + 64;                // [64] sin(2 pi m / n)
+    float* win = tw_s + 64;                 // [64] periodic Hann(63)
+    float* fb = win + 64;                   // [32][64]
+    float* pw = fb + MEL_BINS * MEL_N;      // [2][frames_chunk = 8][32] power spectra
+    __shared__ double red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < T; i += blockDim.x) { xp[i] = env[((size_t)b * 2) * T + i]; xt[i] = env[((size_t)b * 2 + 1) * T + i]; }
+    for (int i = tid; i < MEL_BINS * MEL_N; i += blockDim.x) fb[i] = mel_fb[i];
+    if (tid < 64) win[tid] = tid < MEL_NFFT ? 0.5f - 0.5f * cospif(2.0f * (float)tid / (float)MEL_NFFT) : 0.f;
+
+    // ---- loss.py:22-35: rectangular-window magnitudes at three scales
+    const int nffts[3] = {63, 32, 16}, hops[3] = {16, 8, 4};
+    for (int s = 0; s < 3; ++s) {
+        const int n = nffts[s], hop = hops[s], pad = n / 2, bins = n / 2 + 1;
+        const int frames = 1 + (T + 2 * pad - n) / hop;
+        __syncthreads();
+        if (tid < n) sincospif(2.0f * (float)tid / (float)n, &tw_s[tid], &tw_c[tid]);
+        __syncthreads();
+        double acc = 0.0;
+        for (int item = tid; item < frames * bins; item += blockDim.x) {
+            const int fr = item / bins, k = item - fr * bins;
+            const int start = fr * hop - pad;
+            float pr = 0.f, pi = 0.f, tr = 0.f, ti = 0.f;
+            int m = 0;                                             // (k * i) mod n, advanced incrementally
+            for (int i = 0; i < n; ++i) {
+                const int idx = start + i;
+                if (idx >= 0 && idx < T) {
+                    const float c = tw_c[m], sn = tw_s[m];
+                    const float a = xp[idx], g = xt[idx];
+                    pr = fmaf(a, c, pr); pi = fmaf(a, sn, pi);
+                    tr = fmaf(g, c, tr); ti = fmaf(g, sn, ti);
+                }
+                m += k; if (m >= n) m -= n;
+            }
+            acc += (double)fabsf(sqrtf(pr * pr + pi * pi) - sqrtf(tr * tr + ti * ti));
+        }
+        const double tot = block_sum(acc, red);
+        if (tid == 0) sums[(size_t)b * 4 + s] = tot;
+    }
+
+    // ---- loss.py:40-69: mel power spectrogram (Hann 63, reflect padding), 8 frames per pass
+    {
+        const int pad = MEL_NFFT / 2;
+        const int frames = 1 + (T + 2 * pad - MEL_NFFT) / MEL_HOP;
+        __syncthreads();
+        if (tid < MEL_NFFT) sincospif(2.0f * (float)tid / (float)MEL_NFFT, &tw_s[tid], &tw_c[tid]);
+        __syncthreads();
+        double acc = 0.0;
+        for (int f0 = 0; f0 < frames; f0 += 8) {
+            const int nf = min(8, frames - f0);
+            // power spectra: item = (signal, frame, bin)
+            for (int item = tid; item < 2 * nf * MEL_BINS; item += blockDim.x) {
+                const int sig = item / (nf * MEL_BINS);
+                const int rem = item - sig * nf * MEL_BINS;
+                const int fr = rem / MEL_BINS, k = rem - fr * MEL_BINS;
+                const float* x = sig ? xt : xp;
+                const int start = (f0 + fr) * MEL_HOP - pad;
+                float re = 0.f, im = 0.f;
+                int m = 0;
+                for (int i = 0; i < MEL_NFFT; ++i) {
+                    int idx = start + i;
+                    if (idx < 0) idx = -idx;                       // reflect (no edge repeat), torch pad_mode='reflect'
+                    if (idx >= T) idx = 2 * (T - 1) - idx;
+                    const float v = x[idx] * win[i];
+                    re = fmaf(v, tw_c[m], re); im = fmaf(v, tw_s[m], im);
+                    m += k; if (m >= MEL_NFFT) m -= MEL_NFFT;
+                }
+                pw[(sig * 8 + fr) * MEL_BINS + k] = re * re + im * im;
+            }
+            __syncthreads();
+            for (int item = tid; item < nf * MEL_N; item += blockDim.x) {
+                const int fr = item / MEL_N, mel = item - fr * MEL_N;
+                float mp = 0.f, mt = 0.f;
+#pragma unroll 8
+                for (int k = 0; k < MEL_BINS; ++k) {
+                    const float w = fb[k * MEL_N + mel];
+                    mp = fmaf(pw[fr * MEL_BINS + k], w, mp);
+                    mt = fmaf(pw[(8 + fr) * MEL_BINS + k], w, mt);
+                }
+                acc += (double)fabsf(mp - mt);
+            }
+            __syncthreads();
+        }
+        const double tot = block_sum(acc, red);
+        if (tid == 0) sums[(size_t)b * 4 + 3] = tot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+__global__ void loss_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ l1_partial, int n_l1, int B, int F,
+                                     int T, float* __restrict__ out4) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double s[4] = {0, 0, 0, 0}, l1 = 0.0;
+    for (int b = 0; b < B; ++b)
+        for (int j = 0; j < 4; ++j) s[j] += sums[(size_t)b * 4 + j];
+    for (int i = 0; i < n_l1; ++i) l1 += l1_partial[i];
+    const int nffts[3] = {63, 32, 16}, hops[3] = {16, 8, 4};
+    double stft = 0.0;
+    for (int j = 0; j < 3; ++j) {
+        const int n = nffts[j], pad = n / 2, bins = n / 2 + 1;
+        const int frames = 1 + (T + 2 * pad - n) / hops[j];
+        stft += s[j] / ((double)B * bins * frames);
+    }
+    stft /= 3.0;
+    const int mframes = 1 + (T + 2 * (MEL_NFFT / 2) - MEL_NFFT) / MEL_HOP;
+    const double mel = s[3] / ((double)B * MEL_N * mframes);
+    const double l1m = l1 / ((double)B * F * T);
+    out4[0] = (float)(0.4 * stft + 0.4 * mel + 0.2 * l1m);
+    out4[1] = (float)stft;
+    out4[2] = (float)mel;
+    out4[3] = (float)l1m;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" int64_t adn_loss_workspace_bytes(int64_t batch, int freq, int frames) {
+    if (batch < 0 || freq <= 0 || frames <= 0) return -1;
+    const size_t env = align256((size_t)batch * 2 * frames * sizeof(float));
+    const size_t l1 = align256((size_t)batch * ((frames + ENV_TX - 1) / ENV_TX) * sizeof(double));
+    const size_t sums = align256((size_t)batch * 4 * sizeof(double));
+    return (int64_t)(env + l1 + sums);
+}
+
+extern "C" int adn_combined_loss_f32(const float* pred, const float* target, int64_t batch, int freq, int frames,
+                                     const float* mel_fb_32x64, void* workspace, float* out4, void* stream) {
+    if (batch <= 0 || freq <= 0 || frames <= 0) return ADN_ERR_ARG;
+    if (!pred || !target || !mel_fb_32x64 || !workspace || !out4) return ADN_ERR_ARG;
+    if (frames > LOSS_MAX_T || frames <= MEL_NFFT / 2 || batch > 65535) return ADN_ERR_ARG;   // reflect padding needs T > 31
+    int st = check_device();
+    if (st != ADN_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    float* env = reinterpret_cast<float*>(ws);
+    const int tx = (frames + ENV_TX - 1) / ENV_TX;
+    double* l1p = reinterpret_cast<double*>(ws + align256((size_t)batch * 2 * frames * sizeof(float)));
+    double* sums = reinterpret_cast<double*>(reinterpret_cast<char*>(l1p) + align256((size_t)batch * tx * sizeof(double)));
+    loss_envelope_kernel<<<dim3(tx, (unsigned)batch), dim3(ENV_TX, ENV_FY), 0, s>>>(pred, target, freq, frames, env, l1p);
+    ADN_LAUNCH_CHECK();
+    const size_t smem = (size_t)(2 * frames + 3 * 64 + MEL_BINS * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float);
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(loss_spectral_kernel, (int)((2 * LOSS_MAX_T + 3 * 64 + MEL_BINS * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float)), smem_set));
+    loss_spectral_kernel<<<(unsigned)batch, 256, smem, s>>>(env, frames, mel_fb_32x64, sums);
+    ADN_LAUNCH_CHECK();
+    loss_finalize_kernel<<<1, 32, 0, s>>>(sums, l1p, (int)(batch * tx), (int)batch, freq, frames, out4);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}

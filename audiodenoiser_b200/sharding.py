@@ -71,20 +71,31 @@ def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def stats_from_sums(sums) -> dict:
-    """[sum|target-pred|, sum target^2, sum (target-pred)^2, count] -> {'l1', 'snr_db', 'count'}.
-    SNR = 10 log10(sum target^2 / sum err^2) on magnitude spectrograms (the reference defines none)."""
+    """[sum|target-pred|, sum target^2, sum (target-pred)^2, count, n_clips, n*stft, n*mel, n*l1] -> metrics.
+    SNR = 10 log10(sum target^2 / sum err^2) on magnitude spectrograms (the reference defines none); the loss
+    terms are the clip-weighted means of CombinedPerceptualLoss (loss.py:83-95), exact for unequal shards."""
     s_abs, s_sig, s_err, cnt = (float(v) for v in sums[:4])
     l1 = s_abs / cnt if cnt > 0 else float("nan")
     snr = 10.0 * math.log10(s_sig / s_err) if s_err > 0 and s_sig > 0 else float("inf")
-    return {"l1": l1, "snr_db": snr, "count": int(cnt)}
+    out = {"l1": l1, "snr_db": snr, "count": int(cnt)}
+    if len(sums) >= 8 and float(sums[4]) > 0:
+        n = float(sums[4])
+        stft, mel, l1m = float(sums[5]) / n, float(sums[6]) / n, float(sums[7]) / n
+        out.update({"loss_total": 0.4 * stft + 0.4 * mel + 0.2 * l1m, "loss_stft": stft, "loss_mel": mel, "loss_l1": l1m,
+                    "clips": int(n)})
+    return out
 
 
 class ShardedDenoiser:
     """One rank's view of the clip-sharded job: denoise the local shard with the single-GPU ``Denoiser``, then gather
     outputs and reduce the error statistics over the group."""
 
-    def __init__(self, denoiser, group=None):
+    def __init__(self, denoiser, group=None, with_loss: bool = True):
         self.denoiser = denoiser
+        self.with_loss = bool(with_loss)
+        if self.with_loss:
+            from .loss import CombinedPerceptualLoss
+            self._criterion = CombinedPerceptualLoss()
         self.group = group
         self.world, self.rank = _world(group)
         self._gather_buf = None
@@ -99,7 +110,7 @@ class ShardedDenoiser:
         if not pred_mag.is_cuda:
             raise _lib.AdnError("error_sums needs CUDA tensors (no CPU fallback)")
         if self._sums is None or self._sums.device != pred_mag.device:
-            self._sums = torch.zeros(4, dtype=torch.float64, device=pred_mag.device)
+            self._sums = torch.zeros(8, dtype=torch.float64, device=pred_mag.device)
         self._sums.zero_()
         p = pred_mag.float().contiguous(); t = target_mag.float().contiguous()
         if p.shape != t.shape:
@@ -108,6 +119,13 @@ class ShardedDenoiser:
             st = _lib.load().adn_spec_error_sums_f64(p.data_ptr(), t.data_ptr(), p.numel(), self._sums.data_ptr(), _lib.stream_ptr())
         _lib.check(st, "adn_spec_error_sums_f64")
         self._sums[3] = float(p.numel())
+        if self.with_loss and p.shape[-1] > 31:
+            # CombinedPerceptualLoss of this shard (test.py:118-122), weighted by its clip count so the reduced value is the
+            # full-batch mean the reference would print
+            terms = self._criterion(p.unsqueeze(1) if p.dim() == 3 else p, t.unsqueeze(1) if t.dim() == 3 else t)
+            n = float(p.shape[0])
+            self._sums[4] = n
+            self._sums[5:8] = torch.stack(terms[1:]).double() * n
         return self._sums
 
     def step(self, wave_local: torch.Tensor, n_total: int, target_mag_local: torch.Tensor | None = None, gather: bool = True):

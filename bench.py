@@ -315,7 +315,7 @@ def run_b200(args):
             if i >= 2:
                 spans["stft"].append((ev[0], ev[1])); spans["istft"].append((ev[2], ev[3]))
         torch.cuda.synchronize()
-        launches_per_step = (net.launch_count - lc0) // reps + 2 + 1        # + stft + istft + error-sums kernel
+        launches_per_step = (net.launch_count - lc0) // reps + 2 + 1 + 3    # + stft + istft + error-sums + 3 loss kernels
         prof = net.profile
         net.profile = None
         agg = {}
@@ -380,7 +380,8 @@ def run_b200(args):
             "kernels": kernels,
             "unet_flops_per_clip": unet_flops(257, t_frames),
             "unet_tflops_in_step": unet_flops(257, t_frames) * batch / (ms_dev / args.steps * 1e-3) / 1e12,
-            "quality": {"snr_db_vs_clean_mag": stats["snr_db"], "l1_vs_clean_mag": stats["l1"], "note": "random-init weights: numbers only prove the statistics path runs"},
+            "quality": {"snr_db_vs_clean_mag": stats["snr_db"], "l1_vs_clean_mag": stats["l1"],
+                        "combined_perceptual_loss": {k: stats.get(k) for k in ("loss_total", "loss_stft", "loss_mel", "loss_l1")}, "note": "random-init weights: numbers only prove the statistics path runs"},
             "cpu_baseline": cpu_baseline,
         }
         emit(line)

@@ -138,6 +138,16 @@ int adn_spec_f16_crop_f32(const float* src, int64_t n, int f_in, int t_in, int f
  * sums is a device array of 3 doubles that the caller zeroes. */
 int adn_spec_error_sums_f64(const float* pred, const float* target, int64_t count, double* sums, void* stream);
 
+/* CombinedPerceptualLoss.forward (loss.py:83-95) = 0.4 * MultiScaleSTFTLoss (loss.py:12-35) + 0.4 * MelSpectrogramLoss
+ * (loss.py:44-69) + 0.2 * L1Loss (loss.py:76,86) on (batch,1,freq,frames) float32 magnitude tensors (test.py:118-122,
+ * train.py:68,85).  out4 (device, 4 floats) = {total, stft, mel, l1}.  mel_fb_32x64: the torchaudio HTK filterbank
+ * melscale_fbanks(32, 0, 4000, 64, 8000, norm=None) as (32, 64) float32 on the device.  workspace: adn_loss_workspace_bytes()
+ * bytes of device scratch, 256-byte aligned.  Requires 31 < frames <= 8192 (reflect padding of the 63-point mel STFT).
+ * Deterministic: ordered two-stage reductions, no atomics. */
+int64_t adn_loss_workspace_bytes(int64_t batch, int freq, int frames);
+int adn_combined_loss_f32(const float* pred, const float* target, int64_t batch, int freq, int frames,
+                          const float* mel_fb_32x64, void* workspace, float* out4, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
