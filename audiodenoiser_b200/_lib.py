@@ -28,6 +28,7 @@ SIGNATURES = {
     "adn_stft_mag_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
     "adn_stft_complex_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
     "adn_istft_ola_f32": (c_int, [P, P, c_int, c_uint64, c_int64, c_int64, P, P]),
+    "adn_random_phasor_c64": (c_int, [c_uint64, c_int64, c_int64, P, P]),
     "adn_stft_mag_host_f32": (c_int, [P, c_int64, c_int64, c_int, P]),
     "adn_istft_ola_host_f32": (c_int, [P, P, c_uint64, c_int64, c_int64, P]),
     "adn_pack_conv3x3_weight_bf16": (c_int, [P, c_int, c_int, P, P]),

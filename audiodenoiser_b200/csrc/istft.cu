@@ -4,43 +4,56 @@
 // Replaces `magnitude_spectrogram * angles` and librosa.istft(hop_length=128) in the reference's
 // griffin_lim_reconstruction (code/test.py:36-37,40,48).
 //
-// Mapping.  One CTA = 256 threads owns S = 29 output hops (3712 samples) of one clip and inverse-transforms the
-// S + 3 = 32 frames that touch them:
-//   1. rows of 32 consecutive frames are read T-contiguously (coalesced) for all 257 bins, multiplied by the
-//      phasor, and transposed into per-frame slots in shared memory;
-//   2. a half-warp inverse-transforms one frame (Hermitian pre-pass -> radix-16 x radix-16 -> window / 256),
-//      writing the 512 windowed samples back over the frame's own slot;
+// Mapping ("lane = frame", the mirror image of stft.cu).  One CTA = 8 warps owns S = 29 output hops (3 712 samples) of
+// one clip and inverse-transforms the S + 3 = 32 frames that touch them; lane t of every warp works on frame tA + t:
+//   1. spectrum rows are read straight from global memory into registers -- 32 consecutive frames of one bin are one
+//      coalesced 128-byte (magnitude) / 256-byte (phasor) request, which is exactly the reference (257, T) layout;
+//      warp w holds the bin columns k = 16 i1 + w and 16 i1 + (16 - w) (0 and 8 for warp 0), i.e. bins k and 256 - k
+//      of the Hermitian pre-pass sit in the SAME thread;
+//   2. pass 1 (radix-16 over i1, conjugate W256 twiddles) -> [o1][i2][frame] work array -> pass 2 (radix-16 over i2)
+//      -> window / 512 -> the frame's 512 samples are parked in a [frame][514]-padded buffer that aliases the work array;
 //   3. every output sample gathers its <= 4 contributions in ascending frame order (deterministic, no atomics),
-//      divides by sum(w^2) over the same frames and is stored with 128-bit writes.
+//      divides by sum(w^2) over the same frames; a warp stores 256 contiguous bytes.
+// Tables (window, twiddles, w^2) are shared-memory arrays read with warp-uniform (broadcast) addresses.
 #include "adn_common.cuh"
 #include "adn_tables.inc"
 
 namespace adn {
 
-constexpr int IS_FRAMES = 32;                 // frames per tile
+constexpr int IS_FRAMES = 32;                 // frames per tile = lanes per warp
 constexpr int IS_HOPS = IS_FRAMES - 3;        // 29 output hops per tile
 constexpr int IS_THREADS = 256;
-constexpr int IS_HALF_WARPS = IS_THREADS / 16;
-constexpr int SLOT = 257;                     // float2 per frame slot: 514 words == 2 (mod 32) -> conflict-free transpose
-constexpr int IXCH_STRIDE = 17;
-constexpr int IXCH_FLOAT2 = 16 * IXCH_STRIDE;
+constexpr int IS_YSTRIDE = 514;               // floats per frame in the sample buffer: 514 mod 32 = 2 -> lane-strided float2 stores hit 32 banks
+constexpr int IS_WORK_BYTES = IS_FRAMES * IS_YSTRIDE * 4;      // 65 792 >= 256 * 32 * 8 (work array)
+constexpr int IS_TABLE_BYTES = 3 * 256 * 8 + 512 * 4 + 128 * 4;
+constexpr int IS_SMEM_BYTES = IS_WORK_BYTES + IS_TABLE_BYTES;
 
-struct IstftSmem {
-    float2 slot[IS_FRAMES][SLOT];             // spectrum in, then 512 windowed samples out (2056 B >= 2048 B)
-    float2 xch[IS_HALF_WARPS][IXCH_FLOAT2];
-    float w2[ADN_N_FFT];
-};
-
-__device__ __forceinline__ float2 random_phasor(unsigned long long seed, unsigned long long idx) {
-    // splitmix64 finaliser as a counter-based generator; 24 random bits -> phase in [0, 1) turns
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const float u = (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// per-clip key of the counter-based phase generator (test.py:36 draws the phase from the unseeded numpy RNG)
+__device__ __forceinline__ uint32_t phase_key(unsigned long long seed, long long clip) {
+    return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) * 0x9E3779B9u + (uint32_t)clip) ^ (uint32_t)((unsigned long long)clip >> 32));
+}
+// 16 random phase bits of bin `row`, frame t of a clip.  One 32-bit hash serves two bins 16 rows apart (rows c + 16 i1 with
+// i1 = 2j, 2j+1), which the iSTFT kernel holds in the same thread.
+__device__ __forceinline__ uint32_t phase_bits(uint32_t key, uint32_t c, uint32_t i1, uint32_t n_frames, uint32_t t) {   // row = c + 16 i1
+    const uint32_t h = mix32(((c + 16u * (i1 >> 1)) * n_frames + t) ^ key);
+    return (i1 & 1u) ? (h >> 16) : (h & 0xffffu);
+}
+__device__ __forceinline__ float2 phasor_from_bits(uint32_t bits16) {
+    const float ang = (float)((int)bits16 - 32768) * (6.283185307179586f / 65536.0f);   // [-pi, pi)
     float s, c;
-    sincospif(2.0f * u, &s, &c);
+    __sincosf(ang, &s, &c);
     return make_float2(c, s);
+}
+
+template <typename T>
+__device__ __forceinline__ const T* is_row_ptr(const T* base, int stride_bytes, int k) {
+    long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride_bytes), "r"(k), "l"(reinterpret_cast<long long>(base)));
+    return reinterpret_cast<const T*>(r);
 }
 
 // MODE 0: spec = mag * phasor ; MODE 1: spec = phasor array itself (complex spectrogram) ; MODE 2: mag * random phasor
@@ -49,120 +62,213 @@ __global__ void __launch_bounds__(IS_THREADS, 2)
 istft_kernel(const float* __restrict__ mag, const float2* __restrict__ ph, unsigned long long seed,
              long long n_clips, int n_frames, int tiles_per_clip, float* __restrict__ audio) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
-    const int tid = threadIdx.x, hw = tid >> 4, j = tid & 15, warp = tid >> 5, lane = tid & 31;
+    float2* const work = reinterpret_cast<float2*>(smem_raw);            // [o1*16 + i2][frame]
+    float* const ybuf = reinterpret_cast<float*>(smem_raw);              // [frame][514], aliases `work`
+    float2* const s_win = reinterpret_cast<float2*>(smem_raw + IS_WORK_BYTES);   // hann[2n], hann[2n+1], each / 512
+    float2* const s_tw256 = s_win + 256;                                 // conj W256^(i2 o1), [i2][o1]
+    float2* const s_tw512 = s_win + 512;                                 // W512^k, k < 256
+    float* const s_w2 = reinterpret_cast<float*>(s_win + 768);           // hann^2 [512]
+    float* const s_wss = s_w2 + 512;                                     // 1 / (interior sum of the four w^2 terms) [128]
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int out_len = ADN_HOP * (n_frames - 1);
-    const unsigned hmask = 0xFFFFu << (16 * (hw & 1));   // half-warps skip invalid frames independently
 
-    for (int i = tid; i < ADN_N_FFT; i += IS_THREADS) { const float w = adn_hann512[i]; sm.w2[i] = w * w; }
-
-    float2 win[16], tw[16];
+    s_win[tid] = make_float2(adn_c_hann512[2 * tid] * (1.0f / 512.0f), adn_c_hann512[2 * tid + 1] * (1.0f / 512.0f));
+    {
+        const float2 t = adn_c_tw256[tid >> 4][tid & 15];
+        s_tw256[tid] = make_float2(t.x, -t.y);
+    }
+    s_tw512[tid] = adn_c_tw512[tid];
+    for (int i = tid; i < ADN_N_FFT; i += IS_THREADS) { const float h = adn_c_hann512[i]; s_w2[i] = h * h; }
+    if (tid < 128) {                                                     // ascending frame order = descending offset
+        float acc = 0.f;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-        // output samples 2*(j+16m), +1 ; the irfft 1/512 normalisation = 1/256 on the packed transform
-        win[m] = make_float2(adn_hann512[32 * m + 2 * j] * (1.0f / 256.0f), adn_hann512[32 * m + 2 * j + 1] * (1.0f / 256.0f));
-        const float2 t = adn_tw256[j][m];
-        tw[m] = make_float2(t.x, -t.y);       // inverse transform: conjugate twiddles
+        for (int q = 0; q < 4; ++q) { const float h = adn_c_hann512[384 - 128 * q + tid]; acc += h * h; }
+        s_wss[tid] = 1.0f / acc;
     }
 
-    const long long total_tiles = n_clips * (long long)tiles_per_clip;
-    for (long long tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
-        const long long clip = tile_id / tiles_per_clip;
-        const int h0 = (int)(tile_id % tiles_per_clip) * IS_HOPS;      // first output hop
-        const int tA = h0 - 1;                                         // first frame of the tile (may be -1)
-        const long long base = clip * (long long)ADN_N_BINS * n_frames;
+    const int a = w, b = (w == 0) ? 8 : 16 - w;
+    const int total_tiles = (int)n_clips * tiles_per_clip;               // < 2^31 (host check)
 
-        // ---- 1. load + transpose: warp per bin row, lanes along frames
+    // Raw spectrum columns a and b of this lane's frame, fetched one tile AHEAD (the loads are issued before the gather
+    // phase of the previous tile and consumed after it, so their latency hides behind it).  Dead lanes (frame outside
+    // [0, T)) load a clamped, in-range address and are zeroed by `vf`: no branches around the loads.
+    float rm[(MODE == 1) ? 1 : 33];
+    float2 rp[(MODE == 2) ? 1 : 33];
+    auto prefetch = [&](int tile) {
+        if (tile >= total_tiles) return;
+        const int clip = tile / tiles_per_clip;
+        const int t = (tile - clip * tiles_per_clip) * IS_HOPS - 1 + lane;
+        const int tc = (t >= 0 && t < n_frames) ? t : 0;
+        const long long base = (long long)clip * ADN_N_BINS * n_frames + tc;   // 257 * T < 2^30 (host check)
+#pragma unroll
+        for (int i1 = 0; i1 < 16; ++i1) {
+            if (MODE != 1) {
+                rm[i1] = __ldcs(is_row_ptr(mag + base + a * n_frames, 16 * n_frames * 4, i1));
+                rm[16 + i1] = __ldcs(is_row_ptr(mag + base + b * n_frames, 16 * n_frames * 4, i1));
+            }
+            if (MODE != 2) {
+                rp[i1] = __ldcs(is_row_ptr(ph + base + a * n_frames, 16 * n_frames * 8, i1));
+                rp[16 + i1] = __ldcs(is_row_ptr(ph + base + b * n_frames, 16 * n_frames * 8, i1));
+            }
+        }
+        if (w == 0) {
+            if (MODE != 1) rm[32] = __ldcs(is_row_ptr(mag + base, 16 * n_frames * 4, 16));
+            if (MODE != 2) rp[32] = __ldcs(is_row_ptr(ph + base, 16 * n_frames * 8, 16));
+        }
+    };
+
+    // Only the magnitude-only mode (33 registers) is fetched ahead; with an explicit phasor the raw tile is 99 registers,
+    // which cannot stay live across the gather without spilling, so modes 0 / 1 load at the top of their own tile.
+    constexpr bool AHEAD = (MODE == 2);
+    if (AHEAD) prefetch(blockIdx.x);
+    for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
+        if (!AHEAD) prefetch(tile_id);
+        const int clip = tile_id / tiles_per_clip;
+        const int h0 = (tile_id - clip * tiles_per_clip) * IS_HOPS;      // first output hop
+        const int tA = h0 - 1;                                           // first frame of the tile (may be -1)
+        const int t = tA + lane;
+        const bool valid = (t >= 0 && t < n_frames);
+        const float vf = valid ? 1.f : 0.f;
+        const int tc = valid ? t : 0;
+        const bool interior = (tA >= 0) && (tA + IS_FRAMES <= n_frames);   // uniform: every frame of the tile exists
+
+        // ---- 1. spectrum columns a and b of frame t: X = mag * phasor
+        float2 A[16], B[16];
+        float x256 = 0.f;                                                // Re X[256] (warp 0)
         {
-            const int t = tA + lane;
-            const bool valid = (t >= 0 && t < n_frames);
-            for (int f = warp; f < ADN_N_BINS; f += IS_THREADS / 32) {
-                float2 x = make_float2(0.f, 0.f);
-                if (valid) {
-                    const long long g = base + (long long)f * n_frames + t;
-                    if (MODE == 1) {
-                        x = __ldcs(ph + g);
-                    } else {
-                        const float m = __ldcs(mag + g);
-                        const float2 p = (MODE == 0) ? __ldcs(ph + g) : random_phasor(seed, (unsigned long long)g);
-                        x = make_float2(m * p.x, m * p.y);
-                    }
-                    if (f == 0 || f == 256) x.y = 0.f;                 // c2r: Im(DC), Im(Nyquist) are ignored
-                }
-                sm.slot[lane][f] = x;
+            uint32_t key = 0;
+            if (MODE == 2) key = phase_key(seed, clip);
+            auto spec = [&](int j, int c, int i1) -> float2 {            // raw slot j = element (c + 16 i1) * T + t
+                if (MODE == 1) return rp[j];
+                const float2 p = (MODE == 0) ? rp[j] : phasor_from_bits(phase_bits(key, (uint32_t)c, (uint32_t)i1, (uint32_t)n_frames, (uint32_t)tc));
+                return make_float2(rm[j] * p.x, rm[j] * p.y);
+            };
+#pragma unroll
+            for (int i1 = 0; i1 < 16; ++i1) { A[i1] = spec(i1, a, i1); B[i1] = spec(16 + i1, b, i1); }
+            if (w == 0) x256 = spec(32, 0, 16).x;
+            if (!interior) {                                             // dead lanes (frames outside [0, T)) contribute zeros
+#pragma unroll
+                for (int i1 = 0; i1 < 16; ++i1) { A[i1].x *= vf; A[i1].y *= vf; B[i1].x *= vf; B[i1].y *= vf; }
+                x256 *= vf;
             }
+        }
+
+        // ---- Hermitian pre-pass in place (unscaled: the 1/2 lives in the window table).  For a pair (k, 256-k):
+        //      E = X[k] + conj X[256-k], D = X[k] - conj X[256-k], O = D conj(W512^k);
+        //      Z[k] = E + iO, Z[256-k] = conj(E) + i conj(O)
+        auto pre = [&](int k, float2& xk, float2& xp) {
+            const float2 e = make_float2(xk.x + xp.x, xk.y - xp.y);
+            const float2 d = make_float2(xk.x - xp.x, xk.y + xp.y);
+            const float2 o = cmul_conj(d, s_tw512[k]);
+            xk = make_float2(e.x - o.y, e.y + o.x);
+            xp = make_float2(e.x + o.y, o.x - e.y);
+        };
+        if (w != 0) {
+#pragma unroll
+            for (int i1 = 0; i1 < 16; ++i1) pre(16 * i1 + a, A[i1], B[15 - i1]);      // 256 - k = 16 (15 - i1) + b
+        } else {
+            A[0] = make_float2(A[0].x + x256, A[0].x - x256);            // k = 0 with 256: c2r ignores Im(DC), Im(Nyquist)
+#pragma unroll
+            for (int i1 = 1; i1 < 8; ++i1) pre(16 * i1, A[i1], A[16 - i1]);
+            A[8] = make_float2(2.f * A[8].x, -2.f * A[8].y);             // k = 128 pairs with itself: Z = 2 conj(X) (unscaled)
+#pragma unroll
+            for (int i1 = 0; i1 < 8; ++i1) pre(16 * i1 + 8, B[i1], B[15 - i1]);
+        }
+
+        // ---- pass 1: inverse radix-16 over i1 for columns i2 = a, b; conjugate W256 twiddles; -> work[o1][i2][frame]
+        dft16<true>(A);
+        dft16<true>(B);
+#pragma unroll
+        for (int o1 = 1; o1 < 16; ++o1) {
+            A[o1] = cmul(A[o1], s_tw256[a * 16 + o1]);
+            B[o1] = cmul(B[o1], s_tw256[b * 16 + o1]);
+        }
+        __syncthreads();                                                 // the previous tile's gather has finished with ybuf
+#pragma unroll
+        for (int o1 = 0; o1 < 16; ++o1) {
+            work[(o1 * 16 + a) * IS_FRAMES + lane] = A[o1];
+            work[(o1 * 16 + b) * IS_FRAMES + lane] = B[o1];
         }
         __syncthreads();
 
-        // ---- 2. inverse transforms: half-warp hw takes frame slots hw, hw+16
-        float2* xch = sm.xch[hw];
-#pragma unroll 1
-        for (int fl = hw; fl < IS_FRAMES; fl += IS_HALF_WARPS) {
-            const int t = tA + fl;
-            if (t < 0 || t >= n_frames) continue;                      // uniform across the half-warp
-            float2* X = sm.slot[fl];
-            float2 v[16];
-            // Hermitian pre-pass: Z[k] = E + iO with E = (X[k] + conj X[256-k])/2, O = conj(W512^k) (X[k] - conj X[256-k])/2
+        // ---- pass 2: rows o1 = w, w + 8 -> z[o1 + 16 o2] = x[2n] + i x[2n+1]; window
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const int k = 16 * n1 + j;
-                const float2 a = X[k];
-                const float2 b = X[256 - k];
-                const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-                const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
-                const float2 o = cmul_conj(d, adn_tw512[k]);
-                v[n1] = make_float2(e.x - o.y, e.y + o.x);             // E + i*O
+        for (int i2 = 0; i2 < 16; ++i2) {
+            A[i2] = work[(w * 16 + i2) * IS_FRAMES + lane];
+            B[i2] = work[((w + 8) * 16 + i2) * IS_FRAMES + lane];
+        }
+        dft16<true>(A);
+        dft16<true>(B);
+        __syncthreads();                                                 // every warp has read its rows: `work` may become `ybuf`
+        {
+            float* yrow = ybuf + lane * IS_YSTRIDE;
+#pragma unroll
+            for (int o2 = 0; o2 < 16; ++o2) {
+                const int n0 = w + 16 * o2, n1 = n0 + 8;
+                const float2 w0 = s_win[n0], w1 = s_win[n1];
+                *reinterpret_cast<float2*>(yrow + 2 * n0) = make_float2(A[o2].x * w0.x, A[o2].y * w0.y);
+                *reinterpret_cast<float2*>(yrow + 2 * n1) = make_float2(B[o2].x * w1.x, B[o2].y * w1.y);
             }
-            __syncwarp(hmask);                                              // all lanes have read X before it is overwritten
-            dft16<true>(v);
-#pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw[k1]);
-#pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) xch[k1 * IXCH_STRIDE + j] = v[k1];
-            __syncwarp(hmask);
-#pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = xch[j * IXCH_STRIDE + n2];
-            __syncwarp(hmask);
-            dft16<true>(v);                                            // z[j + 16*m] = x[2(j+16m)] + i x[2(j+16m)+1]
-#pragma unroll
-            for (int m = 0; m < 16; ++m) X[j + 16 * m] = make_float2(v[m].x * win[m].x, v[m].y * win[m].y);
         }
         __syncthreads();
+        if (AHEAD) prefetch(tile_id + gridDim.x);                        // in flight during the gather below (A, B are dead here)
 
         // ---- 3. gather overlap-add: sample n = 128*h + r, padded position p = n + 256 = 128*(h+2) + r,
-        //         contributions from frames t = h-1 .. h+2 at offsets 384+r, 256+r, 128+r, r
+        //         contributions from frames t = h-1 .. h+2 at offsets 384+r, 256+r, 128+r, r (dead frames hold zeros)
         const int hops = min(IS_HOPS, (n_frames - 1) - h0);
-        float* __restrict__ dst = audio + clip * (long long)out_len + (long long)h0 * ADN_HOP;
-        for (int i = tid * 4; i < hops * ADN_HOP; i += IS_THREADS * 4) {
-            const int hl = i >> 7, r = i & 127;                        // local hop, offset within hop (multiple of 4)
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), wss = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* __restrict__ dst = audio + (long long)clip * out_len + h0 * ADN_HOP;
+        {
+            const int hq = tid >> 6, r = (tid & 63) * 2;                 // this thread: hops hq, hq+4, ... ; offset r (even)
+            const float* yb = ybuf + hq * IS_YSTRIDE + 384 + r;
+            float* d = dst + hq * ADN_HOP + r;
+            if (interior) {
+                const float2 inv = *reinterpret_cast<const float2*>(&s_wss[r]);     // 1 / sum of the four w^2 terms
+                for (int hl = hq; hl < hops; hl += 4, yb += 4 * IS_YSTRIDE, d += 4 * ADN_HOP) {
+                    float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                              // frame slot hl + q  <->  t = h0 + hl - 1 + q
-                const int t = tA + hl + q;
-                if (t >= 0 && t < n_frames) {
-                    const int off = 384 - 128 * q + r;
-                    const float2* ys = &sm.slot[hl + q][off >> 1];     // slots are only 8-byte aligned (257 float2)
-                    const float2 y0 = ys[0], y1 = ys[1];
-                    const float4 w = *reinterpret_cast<const float4*>(&sm.w2[off]);
-                    acc.x += y0.x; acc.y += y0.y; acc.z += y1.x; acc.w += y1.y;
-                    wss.x += w.x; wss.y += w.y; wss.z += w.z; wss.w += w.w;
+                    for (int q = 0; q < 4; ++q) {                        // frame slot hl + q  <->  t = h0 + hl - 1 + q
+                        const float2 y = *reinterpret_cast<const float2*>(yb + q * (IS_YSTRIDE - 128));
+                        acc.x += y.x; acc.y += y.y;
+                    }
+                    __stcs(reinterpret_cast<float2*>(d), make_float2(acc.x * inv.x, acc.y * inv.y));
+                }
+            } else {
+                for (int hl = hq; hl < hops; hl += 4, yb += 4 * IS_YSTRIDE, d += 4 * ADN_HOP) {
+                    float2 acc = make_float2(0.f, 0.f), wss = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 y = *reinterpret_cast<const float2*>(yb + q * (IS_YSTRIDE - 128));
+                        acc.x += y.x; acc.y += y.y;
+                        const int tq = tA + hl + q;
+                        if (tq >= 0 && tq < n_frames) {
+                            const float2 ww = *reinterpret_cast<const float2*>(&s_w2[384 - 128 * q + r]);
+                            wss.x += ww.x; wss.y += ww.y;
+                        }
+                    }
+                    const float tiny = 1.17549435e-38f;
+                    __stcs(reinterpret_cast<float2*>(d), make_float2(wss.x > tiny ? acc.x / wss.x : acc.x, wss.y > tiny ? acc.y / wss.y : acc.y));
                 }
             }
-            const float tiny = 1.17549435e-38f;
-            float4 o;
-            o.x = wss.x > tiny ? acc.x / wss.x : acc.x;
-            o.y = wss.y > tiny ? acc.y / wss.y : acc.y;
-            o.z = wss.z > tiny ? acc.z / wss.z : acc.z;
-            o.w = wss.w > tiny ? acc.w / wss.w : acc.w;
-            __stcs(reinterpret_cast<float4*>(dst + i), o);
         }
-        __syncthreads();
+        // the next tile's first barrier (before its work[] stores) orders this gather against them
+    }
+}
+
+__global__ void random_phasor_kernel(unsigned long long seed, long long n_clips, int n_frames, float2* __restrict__ out) {
+    const int per_clip = ADN_N_BINS * n_frames;
+    const long long total = n_clips * per_clip;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long clip = i / per_clip;
+        const int e = (int)(i - clip * per_clip), row = e / n_frames, t = e - row * n_frames;
+        out[i] = phasor_from_bits(phase_bits(phase_key(seed, clip), (uint32_t)(row & 15), (uint32_t)(row >> 4), (uint32_t)n_frames, (uint32_t)t));
     }
 }
 
 static int launch_istft(const float* mag, const float* phasor, int spec_is_complex, uint64_t seed, int64_t n_clips,
                         int64_t n_frames, float* audio, cudaStream_t stream) {
-    if (n_clips < 0 || n_frames < 1 || n_frames > ((int64_t)1 << 23)) return ADN_ERR_ARG;
+    if (n_clips < 0 || n_frames < 1 || n_frames * ADN_N_BINS >= ((int64_t)1 << 31) / 2) return ADN_ERR_ARG;   // 32-bit per-clip byte offsets
     if (n_clips == 0 || n_frames == 1) return ADN_OK;          // hop*(T-1) = 0 samples
     if (!audio) return ADN_ERR_ARG;
     if (spec_is_complex ? !phasor : !mag) return ADN_ERR_ARG;
@@ -172,8 +278,9 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
     const int hops_total = (int)n_frames - 1;
     const int tiles_per_clip = (hops_total + IS_HOPS - 1) / IS_HOPS;
     const long long total = (long long)n_clips * tiles_per_clip;
-    const size_t smem = sizeof(IstftSmem);
-    const long long max_grid = (long long)num_sms() * 2 * 8;
+    if (total >= ((int64_t)1 << 31) - 4096) return ADN_ERR_ARG;
+    const size_t smem = IS_SMEM_BYTES;
+    const long long max_grid = (long long)num_sms() * 2;       // persistent: 2 resident CTAs per SM loop over the tiles
     const int grid = (int)(total < max_grid ? total : max_grid);
     const float2* ph = reinterpret_cast<const float2*>(phasor);
 #define ADN_ISTFT_LAUNCH(MODE)                                                                                     \
@@ -196,4 +303,18 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
 extern "C" int adn_istft_ola_f32(const float* mag, const float* phasor_c64, int spec_is_complex, uint64_t seed,
                                  int64_t n_clips, int64_t n_frames, float* audio, void* stream) {
     return adn::launch_istft(mag, phasor_c64, spec_is_complex, seed, n_clips, n_frames, audio, (cudaStream_t)stream);
+}
+
+extern "C" int adn_random_phasor_c64(uint64_t seed, int64_t n_clips, int64_t n_frames, float* phasor_c64, void* stream) {
+    if (n_clips < 0 || n_frames < 1 || n_frames * ADN_N_BINS >= ((int64_t)1 << 31) / 2) return ADN_ERR_ARG;
+    if (n_clips == 0) return ADN_OK;
+    if (!phasor_c64) return ADN_ERR_ARG;
+    int st = adn::check_device();
+    if (st != ADN_OK) return st;
+    const long long total = n_clips * n_frames * ADN_N_BINS;
+    const long long want = (total + 255) / 256, cap = (long long)adn::num_sms() * 16;
+    adn::random_phasor_kernel<<<(int)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(
+        (unsigned long long)seed, n_clips, (int)n_frames, reinterpret_cast<float2*>(phasor_c64));
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
 }

@@ -3,163 +3,239 @@
 // Replaces librosa.stft + librosa.magphase at code/create_train_dataset.py:167-173 (center=False) and
 // code/create_test_dataset.py:39-40 (center=True, zero padding) of the reference.
 //
-// Mapping.  One CTA = 256 threads = 16 half-warps owns a tile of TF = 32 consecutive frames of one clip.
-//   1. the (TF-1)*128+512 contiguous samples the tile touches are staged once in shared memory (frames overlap
-//      by 75 %, so each sample is reused 4x from smem, read once from HBM), 128-bit loads when aligned, zero
-//      fill for the centred edges;
-//   2. a half-warp transforms one frame: the 512 real samples are packed as 256 complex points, 16 per lane,
-//      register-resident radix-16 x radix-16 with one shared-memory exchange between the passes, then the
-//      real-FFT split produces bins k and 256-k together;
-//   3. magnitudes are parked in a [257][TF] shared tile and written out as T-contiguous row segments, which is
-//      the reference .npy layout (257, T).
-// Window and twiddles are compile-time float32 tables (adn_tables.inc), held in registers across tiles.
+// Mapping ("lane = frame").  One CTA = 8 warps owns a tile of TF = 32 consecutive frames of one clip; lane t of every
+// warp works on frame t0 + t, so every shared-memory access of the transform is [point][frame] (conflict-free by
+// construction) and every global store is a run of 32 consecutive frames of one bin row -- the reference .npy layout
+// (257, T) with T contiguous -- straight from registers, with no output transpose.
+//   1. the 35 hops (4 480 samples) the tile touches are staged once with cp.async into a [hop][130]-padded buffer
+//      (frames overlap by 75 %: each sample is read once from HBM and 4x from shared memory; the pad makes the
+//      lane-strided float2 reads conflict-free), zero fill for the centred edges; the NEXT tile's samples are in flight
+//      (second buffer) while this tile is transformed;
+//   2. the 512 real samples of a frame are packed as 256 complex points, n = 16 n1 + n2.  Pass 1: warp w transforms the
+//      columns n2 = w, w + 8 (radix-16 in registers, window folded into the load, W256 twiddles) into a
+//      [k1][n2][frame] work array.  Pass 2: warp w transforms the rows k1 = w and 16 - w (0 and 8 for warp 0), which
+//      hold bins k and 256 - k of the real-FFT split in the SAME thread, so the split, the magnitude and the store need
+//      no further exchange.
+// Window / twiddle tables are indexed by warp-uniform values only (broadcast shared-memory loads): no registers are
+// spent on them, so pass 2 can hold two rows (64 registers) per thread.
 #include "adn_common.cuh"
 #include "adn_tables.inc"
 
 namespace adn {
 
-constexpr int TF = 32;                                   // frames per tile
+constexpr int TF = 32;                                   // frames per tile = lanes per warp
 constexpr int STFT_THREADS = 256;
-constexpr int HALF_WARPS = STFT_THREADS / 16;
-constexpr int TILE_SAMPLES = (TF - 1) * ADN_HOP + ADN_N_FFT;   // 4480
-constexpr int XCH_STRIDE = 17;                           // float2 row stride of the 16x16 exchange (conflict-free)
-constexpr int XCH_FLOAT2 = 16 * XCH_STRIDE;              // 272 >= 256 (also holds Z[0..255] for the split)
-constexpr int MAG_STRIDE = TF + 2;                       // 34: (2k + t) mod 32 distinct across a warp
+constexpr int ST_ROWS = TF + 3;                          // hops touched by a tile
+constexpr int ST_ROW_STRIDE = 130;                       // floats; 130 mod 32 = 2 -> lane-strided float2 reads hit 32 banks
+constexpr int ST_SAMPLES_BYTES = (ST_ROWS * ST_ROW_STRIDE * 4 + 15) / 16 * 16;
+constexpr int ST_WORK_BYTES = 256 * TF * 8;
+constexpr int ST_TABLE_BYTES = 3 * 256 * 8;             // 0.5*hann as float2[256], W256^(n2 k1) [16][16], W512^k [256]
+constexpr int ST_SMEM_BYTES = 2 * ST_SAMPLES_BYTES + ST_WORK_BYTES + ST_TABLE_BYTES;
 
-template <bool COMPLEX_OUT>
-struct StftSmem {
-    float samples[TILE_SAMPLES];
-    float2 xch[HALF_WARPS][XCH_FLOAT2];
-    float tile[COMPLEX_OUT ? 2 : 1][ADN_N_BINS * MAG_STRIDE];   // re (and im) planes, [bin][frame]
-};
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// base + k * stride_bytes as ONE IMAD.WIDE (k folds to an immediate after unrolling)
+template <typename T>
+__device__ __forceinline__ T* row_ptr(T* base, int stride_bytes, int k) {
+    long long r;
+    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(stride_bytes), "r"(k), "l"(reinterpret_cast<long long>(base)));
+    return reinterpret_cast<T*>(r);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// samples [s0, s0 + 128 * rows) of one clip -> buf[row][0..127], zero outside [0, length); s0 is a multiple of 128.
+// Interior full tiles (the common case) take a path whose addresses are all immediates: thread `tid` copies the pair at
+// column 2 (tid & 63) of rows (tid >> 6) + 4 i.
+__device__ __forceinline__ void stft_stage(float* buf, const float* __restrict__ src, const float* dummy, int s0,
+                                           int length, int rows, int tid) {
+    const bool al8 = (reinterpret_cast<uintptr_t>(src) & 7) == 0;
+    if (al8 && rows == ST_ROWS && s0 >= 0 && s0 + ST_ROWS * ADN_HOP <= length) {
+        const float* g = src + s0 + (tid >> 6) * ADN_HOP + ((tid & 63) << 1);
+        const uint32_t dst = st_smem_u32(buf + (tid >> 6) * ST_ROW_STRIDE + ((tid & 63) << 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cp_async8(dst + i * 4 * ST_ROW_STRIDE * 4, g + i * 4 * ADN_HOP, 8);
+        if (tid < 64 * (ST_ROWS - 32)) cp_async8(dst + 8 * 4 * ST_ROW_STRIDE * 4, g + 8 * 4 * ADN_HOP, 8);
+        return;
+    }
+    if (length <= 0) src = dummy;                        // nothing is read (src-size 0), but keep the address valid
+    const int g_last = (length - 1) & ~1;                // clamp target: even (8-byte aligned when src is) and in range
+    for (int p = tid; p < rows * 64; p += STFT_THREADS) {
+        const int row = p >> 6, c = (p & 63) << 1;
+        const int g = s0 + row * ADN_HOP + c;
+        const uint32_t dst = st_smem_u32(buf + row * ST_ROW_STRIDE + c);
+        const bool ok0 = (unsigned)g < (unsigned)length, ok1 = (unsigned)(g + 1) < (unsigned)length;
+        const float* sp = src + max(0, min(g, g_last));
+        if (al8) {                                       // g is even: ok1 implies ok0
+            cp_async8(dst, sp, ok0 ? (ok1 ? 8 : 4) : 0);
+        } else {
+            cp_async4(dst, sp, ok0 ? 4 : 0);
+            cp_async4(dst + 4, ok1 ? sp + 1 : sp, ok1 ? 4 : 0);
+        }
+    }
+}
 
 template <bool COMPLEX_OUT>
 __global__ void __launch_bounds__(STFT_THREADS, 2)
-stft_kernel(const float* __restrict__ wave, long long n_clips, long long length, long long clip_stride, int center,
+stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long long clip_stride, int center,
             int n_frames, int tiles_per_clip, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    StftSmem<COMPLEX_OUT>& sm = *reinterpret_cast<StftSmem<COMPLEX_OUT>*>(smem_raw);
+    float* const samples0 = reinterpret_cast<float*>(smem_raw);
+    float* const samples1 = reinterpret_cast<float*>(smem_raw + ST_SAMPLES_BYTES);
+    float2* const work = reinterpret_cast<float2*>(smem_raw + 2 * ST_SAMPLES_BYTES);   // [k1*16 + n2][frame]
+    // tables in shared memory, read with warp-uniform addresses (broadcast, one wavefront each).  Indexed __constant__
+    // loads were measured to miss the SM's small constant cache and saturate the GPC-level one (ncu gcc__ 57 %).
+    float2* const s_hann = reinterpret_cast<float2*>(smem_raw + 2 * ST_SAMPLES_BYTES + ST_WORK_BYTES);
+    float2* const s_tw256 = s_hann + 256;
+    float2* const s_tw512 = s_hann + 512;
 
-    const int tid = threadIdx.x;
-    const int hw = tid >> 4;        // half-warp index 0..15
-    const int j = tid & 15;         // lane within the half-warp
-    const int warp = tid >> 5, lane = tid & 31;
-    const unsigned hmask = 0xFFFFu << (16 * (hw & 1));   // the two half-warps of a warp run independent frame loops
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp index, provably warp-uniform for the compiler
+    s_hann[tid] = adn_c_hann512_half[tid];
+    s_tw256[tid] = adn_c_tw256[tid >> 4][tid & 15];
+    s_tw512[tid] = adn_c_tw512[tid];
+    const int total_tiles = (int)n_clips * tiles_per_clip;        // < 2^31 (host check)
+    const int pad = center ? ADN_N_FFT / 2 : 0;
 
-    // thread-constant tables: window at the samples this lane packs, pass-1 twiddles W256^(j*k1)
-    float2 win[16];
-    float2 tw[16];
-#pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) {
-        win[n1] = make_float2(adn_hann512[32 * n1 + 2 * j], adn_hann512[32 * n1 + 2 * j + 1]);
-        tw[n1] = adn_tw256[j][n1];
-    }
-
-    const long long total_tiles = n_clips * (long long)tiles_per_clip;
-    for (long long tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
-        const long long clip = tile_id / tiles_per_clip;
-        const int t0 = (int)(tile_id % tiles_per_clip) * TF;
+    auto stage = [&](int clip, int t0, float* buf) {
         const int nf = min(TF, n_frames - t0);
-        const float* __restrict__ src = wave + clip * clip_stride;
-        const long long s0 = (long long)t0 * ADN_HOP - (center ? ADN_N_FFT / 2 : 0);
-        const int need = (nf - 1) * ADN_HOP + ADN_N_FFT;
+        stft_stage(buf, wave + clip * clip_stride, out, t0 * ADN_HOP - pad, length, nf + 3, tid);
+    };
 
-        // ---- 1. stage samples [s0, s0 + need) with zero fill outside [0, length)
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);   // s0 is a multiple of 128
-        if (vec_ok) {
-            for (int i = tid * 4; i < need; i += STFT_THREADS * 4) {
-                const long long g = s0 + i;
-                float4 v;
-                if (g >= 0 && g + 3 < length) {
-                    v = __ldg(reinterpret_cast<const float4*>(src + g));
-                } else {
-                    v.x = (g >= 0 && g < length) ? src[g] : 0.f;
-                    v.y = (g + 1 >= 0 && g + 1 < length) ? src[g + 1] : 0.f;
-                    v.z = (g + 2 >= 0 && g + 2 < length) ? src[g + 2] : 0.f;
-                    v.w = (g + 3 >= 0 && g + 3 < length) ? src[g + 3] : 0.f;
-                }
-                *reinterpret_cast<float4*>(&sm.samples[i]) = v;
-            }
-        } else {
-            for (int i = tid; i < need; i += STFT_THREADS) {
-                const long long g = s0 + i;
-                sm.samples[i] = (g >= 0 && g < length) ? src[g] : 0.f;
-            }
+    int tile_id = blockIdx.x;
+    int clip = tile_id / tiles_per_clip, t0 = (tile_id - clip * tiles_per_clip) * TF;
+    if (tile_id < total_tiles) stage(clip, t0, samples0);
+    cp_async_commit();
+    int parity = 0;
+    for (; tile_id < total_tiles; tile_id += gridDim.x, parity ^= 1) {
+        const float* cur = parity ? samples1 : samples0;
+        const int nf = min(TF, n_frames - t0);
+        const int cur_clip = clip, cur_t0 = t0;
+        {                                                         // decompose the next tile once; it becomes `cur` next round
+            const int nxt = tile_id + gridDim.x;
+            clip = nxt / tiles_per_clip;
+            t0 = (nxt - clip * tiles_per_clip) * TF;
         }
-        __syncthreads();
+        cp_async_wait_all();
+        __syncthreads();             // samples of this tile visible; every warp is done with `work` of the previous tile
 
-        // ---- 2. transforms: half-warp hw takes frames hw, hw+16
-        float2* xch = sm.xch[hw];
-#pragma unroll 1
-        for (int fl = hw; fl < nf; fl += HALF_WARPS) {
-            const float* fr = &sm.samples[fl * ADN_HOP];
-            float2 v[16];
+        // ---- pass 1: columns n2 = w, w + 8 of frame t0 + lane
+        const float* fr = cur + lane * ST_ROW_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int n2 = w + 8 * c;
+            float2 v[16], tw[16];
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
-                const float2 s = *reinterpret_cast<const float2*>(fr + 32 * n1 + 2 * j);
-                v[n1] = make_float2(s.x * win[n1].x, s.y * win[n1].y);
+                const float2 s = *reinterpret_cast<const float2*>(fr + (n1 >> 2) * ST_ROW_STRIDE + 32 * (n1 & 3) + 2 * n2);
+                const float2 wn = s_hann[16 * n1 + n2];
+                v[n1] = make_float2(s.x * wn.x, s.y * wn.y);
             }
-            dft16<false>(v);                       // over n1: Y[k1][n2 = j]
+#pragma unroll
+            for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw256[n2 * 16 + k1];   // in flight during the butterflies
+            dft16<false>(v);                                     // over n1: Y[k1]
 #pragma unroll
             for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw[k1]);
 #pragma unroll
-            for (int k1 = 0; k1 < 16; ++k1) xch[k1 * XCH_STRIDE + j] = v[k1];
-            __syncwarp(hmask);
-#pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = xch[j * XCH_STRIDE + n2];   // lane j now plays k1 = j
-            __syncwarp(hmask);
-            dft16<false>(v);                       // over n2: Z[j + 16*k2]
-#pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) xch[j + 16 * k2] = v[k2];
-            __syncwarp(hmask);
-            // real-FFT split: X[k] = E + W512^k O ; conj(X[256-k]) = E - W512^k O
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int k = j + 16 * m;          // 0..127
-                const float2 a = xch[k];
-                const float2 b = xch[(256 - k) & 255];
-                const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-                const float2 o = make_float2(0.5f * (a.y + b.y), 0.5f * (b.x - a.x));   // -i/2 (a - conj b)
-                const float2 wo = cmul(o, adn_tw512[k]);
-                const float2 xk = cadd(e, wo);
-                const float2 xn = csub(e, wo);     // conj of X[256-k]
-                if (COMPLEX_OUT) {
-                    sm.tile[0][k * MAG_STRIDE + fl] = xk.x;
-                    sm.tile[COMPLEX_OUT ? 1 : 0][k * MAG_STRIDE + fl] = xk.y;
-                    sm.tile[0][(256 - k) * MAG_STRIDE + fl] = xn.x;
-                    sm.tile[COMPLEX_OUT ? 1 : 0][(256 - k) * MAG_STRIDE + fl] = -xn.y;
-                } else {
-                    sm.tile[0][k * MAG_STRIDE + fl] = sqrtf(fmaf(xk.x, xk.x, xk.y * xk.y));
-                    sm.tile[0][(256 - k) * MAG_STRIDE + fl] = sqrtf(fmaf(xn.x, xn.x, xn.y * xn.y));
-                }
-            }
-            if (j == 0) {                          // k = 128 pairs with itself: X[128] = conj(Z[128])
-                const float2 a = xch[128];
-                if (COMPLEX_OUT) {
-                    sm.tile[0][128 * MAG_STRIDE + fl] = a.x;
-                    sm.tile[COMPLEX_OUT ? 1 : 0][128 * MAG_STRIDE + fl] = -a.y;
-                } else {
-                    sm.tile[0][128 * MAG_STRIDE + fl] = sqrtf(fmaf(a.x, a.x, a.y * a.y));
-                }
-            }
-            __syncwarp(hmask);
+            for (int k1 = 0; k1 < 16; ++k1) work[(k1 * 16 + n2) * TF + lane] = v[k1];
         }
+
+        // next tile's samples stream into the other buffer while this tile finishes
+        if (tile_id + gridDim.x < total_tiles) stage(clip, t0, parity ? samples0 : samples1);
+        cp_async_commit();
         __syncthreads();
 
-        // ---- 3. write the tile: one warp per bin row, lanes along frames (T-contiguous output)
-        if (COMPLEX_OUT) {
-            float2* __restrict__ dst = reinterpret_cast<float2*>(out) + (clip * ADN_N_BINS) * (long long)n_frames + t0;
-            for (int f = warp; f < ADN_N_BINS; f += STFT_THREADS / 32)
-                if (lane < nf)
-                    __stcs(dst + (long long)f * n_frames + lane,
-                           make_float2(sm.tile[0][f * MAG_STRIDE + lane], sm.tile[COMPLEX_OUT ? 1 : 0][f * MAG_STRIDE + lane]));
+        // ---- pass 2 + real-FFT split.  Z = half-scale packed transform; for a pair (k, 256-k):
+        //      E = Zk + conj(Zp), O = -i (Zk - conj(Zp)), X[k] = E + W512^k O, conj(X[256-k]) = E - W512^k O
+        const bool live = lane < nf;
+        const int a = w, b = (w == 0) ? 8 : 16 - w;
+        float2 A[16], B[16];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) A[n2] = work[(a * 16 + n2) * TF + lane];
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) B[n2] = work[(b * 16 + n2) * TF + lane];
+        dft16<false>(A);                                         // A[k2] = Z[a + 16 k2]
+        dft16<false>(B);                                         // B[k2] = Z[b + 16 k2]
+        // split in place: zk <- X[k], zp <- conj(X[256-k])
+        auto split = [&](int k, float2& zk, float2& zp) {
+            const float2 e = make_float2(zk.x + zp.x, zk.y - zp.y);
+            const float2 o = make_float2(zk.y + zp.y, zp.x - zk.x);
+            const float2 wo = cmul(o, s_tw512[k]);
+            zk = cadd(e, wo);
+            zp = csub(e, wo);
+        };
+        if (w != 0) {
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) split(a + 16 * k2, A[k2], B[15 - k2]);   // 256 - k = b + 16 (15 - k2)
         } else {
-            float* __restrict__ dst = out + (clip * ADN_N_BINS) * (long long)n_frames + t0;
-            for (int f = warp; f < ADN_N_BINS; f += STFT_THREADS / 32)
-                if (lane < nf) __stcs(dst + (long long)f * n_frames + lane, sm.tile[0][f * MAG_STRIDE + lane]);
+            {                                                    // bins 0 and 256 (real): X[0] = 2(Re + Im), X[256] = 2(Re - Im)
+                const float2 z = A[0];
+                A[0] = make_float2(2.f * (z.x + z.y), 2.f * (z.x - z.y));
+            }
+#pragma unroll
+            for (int k2 = 1; k2 < 8; ++k2) split(16 * k2, A[k2], A[16 - k2]);
+            A[8] = make_float2(2.f * A[8].x, -2.f * A[8].y);     // k = 128 pairs with itself: X[128] = 2 conj(Z[128])
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) split(8 + 16 * k2, B[k2], B[15 - k2]);
         }
-        __syncthreads();
+        // Where the values live now (row = bin):
+        //   w != 0: A[k2] = X[a + 16 k2], B[j] = conj X[b + 16 j]
+        //   w == 0: A[0] = (X[0], X[256]); A[k2<8] = X[16 k2]; A[8] = X[128]; A[k2>8] = conj X[16 k2];
+        //           B[k2<8] = X[8 + 16 k2]; B[k2>=8] = conj X[8 + 16 k2]
+        const long long row0 = ((long long)cur_clip * ADN_N_BINS) * n_frames + cur_t0 + lane;   // 257 * T < 2^31 (host check)
+        const int s16 = 16 * n_frames * (COMPLEX_OUT ? 8 : 4);   // bytes between rows k and k + 16
+        if (COMPLEX_OUT) {
+            float2* const pa = reinterpret_cast<float2*>(out) + row0 + a * n_frames;
+            float2* const pb = reinterpret_cast<float2*>(out) + row0 + b * n_frames;
+            if (live) {
+                if (w != 0) {
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        __stcs(row_ptr(pa, s16, k2), A[k2]);
+                        __stcs(row_ptr(pb, s16, k2), make_float2(B[k2].x, -B[k2].y));
+                    }
+                } else {
+                    __stcs(pa, make_float2(A[0].x, 0.f));
+                    __stcs(row_ptr(pa, s16, 16), make_float2(A[0].y, 0.f));
+#pragma unroll
+                    for (int k2 = 1; k2 < 16; ++k2) __stcs(row_ptr(pa, s16, k2), make_float2(A[k2].x, k2 > 8 ? -A[k2].y : A[k2].y));
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) __stcs(row_ptr(pb, s16, k2), make_float2(B[k2].x, k2 >= 8 ? -B[k2].y : B[k2].y));
+                }
+            }
+        } else {
+            float* const pa = out + row0 + a * n_frames;
+            float* const pb = out + row0 + b * n_frames;
+            float ma[16], mb[16];
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+                ma[k2] = sqrt_approx(fmaf(A[k2].x, A[k2].x, A[k2].y * A[k2].y));
+                mb[k2] = sqrt_approx(fmaf(B[k2].x, B[k2].x, B[k2].y * B[k2].y));
+            }
+            if (live) {
+                if (w == 0) {
+                    __stcs(row_ptr(pa, s16, 16), fabsf(A[0].y));
+                    ma[0] = fabsf(A[0].x);
+                }
+#pragma unroll
+                for (int k2 = 0; k2 < 16; ++k2) {
+                    __stcs(row_ptr(pa, s16, k2), ma[k2]);
+                    __stcs(row_ptr(pb, s16, k2), mb[k2]);
+                }
+            }
+        }
     }
+    cp_async_wait_all();
 }
 
 template <bool COMPLEX_OUT>
@@ -170,18 +246,19 @@ static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64
     if (T < 0) return ADN_ERR_SHORT;
     if (n_clips == 0) return ADN_OK;
     if ((!wave && length > 0) || !out) return ADN_ERR_ARG;      // an empty centred clip still yields one zero frame
-    if (T > (int64_t)1 << 30) return ADN_ERR_ARG;
+    if (length >= ((int64_t)1 << 30) || T * ADN_N_BINS >= ((int64_t)1 << 31)) return ADN_ERR_ARG;   // 32-bit per-clip offsets
     int st = check_device();
     if (st != ADN_OK) return st;
     const int tiles_per_clip = (int)((T + TF - 1) / TF);
     const long long total = (long long)n_clips * tiles_per_clip;
-    const size_t smem = sizeof(StftSmem<COMPLEX_OUT>);
+    if (total >= ((int64_t)1 << 31) - 4096) return ADN_ERR_ARG;
+    const size_t smem = ST_SMEM_BYTES;
     auto kern = stft_kernel<COMPLEX_OUT>;
     static unsigned char smem_set[64] = {0};
     ADN_CUDA_TRY(ensure_dyn_smem(kern, (int)smem, smem_set));
-    const long long max_grid = (long long)num_sms() * 2 * 8;     // 2 resident CTAs per SM, 8 waves before looping
+    const long long max_grid = (long long)num_sms() * 2;         // persistent: 2 resident CTAs per SM loop over the tiles
     const int grid = (int)(total < max_grid ? total : max_grid);
-    kern<<<grid, STFT_THREADS, smem, stream>>>(wave, n_clips, length, clip_stride, center, (int)T, tiles_per_clip, out);
+    kern<<<grid, STFT_THREADS, smem, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, tiles_per_clip, out);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

@@ -107,3 +107,15 @@ def istft_batched(mag, phasor=None, seed: int = 0, out=None):
                                            out.data_ptr(), _lib.stream_ptr())
     _lib.check(st, "adn_istft_ola_f32")
     return out
+
+
+def random_phasor(seed: int, n_clips: int, n_frames: int, device=None):
+    """The (n_clips, 257, T) complex64 unit phasor ``istft_batched(mag, None, seed)`` applies: the seeded device-side
+    stand-in for ``np.exp(2j * np.pi * np.random.rand(*mag.shape))`` (test.py:36)."""
+    torch = _lib.require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.empty((int(n_clips), N_BINS, int(n_frames)), dtype=torch.complex64, device=device)
+    with torch.cuda.device(device):
+        st = _lib.load().adn_random_phasor_c64(int(seed) & 0xFFFFFFFFFFFFFFFF, int(n_clips), int(n_frames), out.data_ptr(), _lib.stream_ptr())
+    _lib.check(st, "adn_random_phasor_c64")
+    return out

@@ -78,6 +78,11 @@ int adn_stft_complex_f32(const float* wave, int64_t n_clips, int64_t length, int
 int adn_istft_ola_f32(const float* mag, const float* phasor_c64, int spec_is_complex, uint64_t seed,
                       int64_t n_clips, int64_t n_frames, float* audio, void* stream);
 
+/* The unit phasor adn_istft_ola_f32 generates for `seed` when phasor == NULL, written out as (n_clips,257,T) complex64:
+ * the device-side stand-in for `angles = np.exp(2j * np.pi * np.random.rand(*mag.shape))` (test.py:36).  Lets a caller
+ * (and the parity tests) reproduce a seeded reconstruction with an explicit phasor, bit for bit. */
+int adn_random_phasor_c64(uint64_t seed, int64_t n_clips, int64_t n_frames, float* phasor_c64, void* stream);
+
 /* Host-buffer variants (pageable or pinned host memory; allocate device scratch internally, synchronise). */
 int adn_stft_mag_host_f32(const float* wave_host, int64_t n_clips, int64_t length, int center, float* mag_host);
 int adn_istft_ola_host_f32(const float* mag_host, const float* phasor_c64_host, uint64_t seed,

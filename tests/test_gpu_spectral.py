@@ -120,6 +120,24 @@ def test_random_phase_is_seeded_and_deterministic():
     assert torch.equal(a, b) and not torch.equal(a, c)
 
 
+def test_random_phase_mode_equals_explicit_phasor():
+    """The in-kernel phase generator is exported (adn_random_phasor_c64): seeded mode == explicit-phasor mode bit for bit,
+    the phasor has unit modulus and uniform phase, and the result matches the oracle istft of mag * phasor."""
+    rng = np.random.default_rng(5)
+    mag = torch.from_numpy(np.abs(rng.standard_normal((3, 257, 70))).astype(np.float32)).to(dev())
+    ph = spectral.random_phasor(42, 3, 70)
+    assert float((ph.abs() - 1).abs().max()) < 1e-5
+    ang = torch.angle(ph).cpu().numpy().ravel()
+    hist = np.histogram(ang, bins=16, range=(-np.pi, np.pi))[0]
+    assert hist.min() > 0.8 * ang.size / 16 and abs(np.mean(np.exp(1j * ang))) < 0.02
+    assert not torch.equal(ph[0], ph[1])                                   # clips get distinct phases
+    a = spectral.istft_batched(mag, None, seed=42)
+    b = spectral.istft_batched(mag, ph)
+    assert torch.equal(a, b)
+    ref = so.istft(mag[1].cpu().numpy().astype(np.float64) * ph[1].cpu().numpy().astype(np.complex128))
+    assert np.max(np.abs(a[1].cpu().numpy() - ref)) <= 1e-5 * np.max(np.abs(ref))
+
+
 # ------------------------------------------------------------------ the reference-named drop-in functions (numpy in/out)
 def test_dropin_audio_to_magnitude_spectrogram():
     x = synth.make_clip(7, "R")[:16000]
