@@ -45,6 +45,27 @@ SIGNATURES = {
     "adn_spec_error_sums_f64": (c_int, [P, P, c_int64, P, P]),
     "adn_loss_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "adn_combined_loss_f32": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, P]),
+    # training step (train.py:65-72)
+    "adn_train_workspace_bytes": (c_int64, []),
+    "adn_conv3x3_affine_bf16": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, P, P]),
+    "adn_conv3x3_c1_affine_bf16": (c_int, [P, c_int, c_int, c_int, P, P, P, c_int, P, P]),
+    "adn_pack_conv3x3_dgrad_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
+    "adn_pack_convt2x2_dgrad_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
+    "adn_bn_train_stats_f32": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P]),
+    "adn_bn_relu_apply_bf16": (c_int, [P, P, P, c_int64, c_int, P, P]),
+    "adn_bn_relu_backward_bf16": (c_int, [P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P, P]),
+    "adn_channel_sum_f32": (c_int, [P, c_int, c_int64, c_int, P, P, P]),
+    "adn_maxpool2x2_backward_add_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "adn_head1x1_forward_f32": (c_int, [P, P, P, c_int64, P, P]),
+    "adn_head1x1_backward": (c_int, [P, P, P, c_int64, P, P, P, P, P]),
+    "adn_conv3x3_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P]),
+    "adn_conv3x3_c1_wgrad_f32": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
+    "adn_convt2x2_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "adn_convt2x2_dgrad_bf16": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P]),
+    "adn_loss_backward_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "adn_combined_loss_backward_f32": (c_int, [P, P, c_int64, c_int, c_int, P, c_float, c_float, c_float, P, P, P]),
+    "adn_grad_norm_f32": (c_int, [P, c_int64, c_float, P, P, P]),
+    "adn_adamw_step_f32": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_int64, P]),
 }
 
 

@@ -40,6 +40,7 @@ struct HaloArgs {
     int c_out, n_blocks, num_tiles;
     int epi;
     int a_stages, b_slots, b_resident;
+    float relu_floor;              // 0 = ReLU, -inf = no activation (train-mode pre-BN output, dgrad)
     int tma_store;                 // epilogue stages bf16 tiles in smem and stores them with TMA (when the smem budget allows)
     const float* scale;
     const float* shift;
@@ -246,7 +247,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 tmem_ld_wait();
                 float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(__uint_as_float(r[i]), t_scale[c0 + i], t_shift[c0 + i]), 0.f);
+                for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(__uint_as_float(r[i]), t_scale[c0 + i], t_shift[c0 + i]), a.relu_floor);
                 if (a.epi == HEPI_HEAD) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[c0 + i], head_acc);
@@ -381,7 +382,7 @@ static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUt
 
 static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
                         const void* w_packed, int c_out, const float* scale, const float* shift, int epi, void* out, void* pool_out,
-                        const float* head_w, const float* head_b, float* head_out, cudaStream_t stream) {
+                        const float* head_w, const float* head_b, float* head_out, cudaStream_t stream, int relu = 1) {
     if (!src0 || !w_packed || !scale || !shift || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     if (c0 <= 0 || (c0 % 64) || c1 < 0 || (c1 % 64) || (c1 > 0 && !src1)) return ADN_ERR_ARG;
     if (c_out <= 0 || (c_out % 64)) return ADN_ERR_ARG;
@@ -403,6 +404,7 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
     args.num_tiles = (int)tiles;
     args.epi = epi;
+    args.relu_floor = relu ? 0.f : -INFINITY;
     args.scale = scale; args.shift = shift;
     args.out = (__nv_bfloat16*)out; args.pool_out = (__nv_bfloat16*)pool_out;
     args.head_w = head_w; args.head_b = head_b; args.head_out = head_out;
@@ -439,6 +441,15 @@ extern "C" int adn_conv3x3_bn_relu_bf16(const void* src0, int c0, const void* sr
                                         void* pool_out, void* stream) {
     return adn::conv3x3_halo(src0, c0, src1, c1, h1, w1, n, h, w, w_packed, c_out, scale, shift, adn::HEPI_NHWC, out, pool_out,
                              nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// Same kernel without the activation: out = conv * scale + shift (train-mode pre-BatchNorm output with scale = 1, shift = conv
+// bias; the data-gradient conv of the backward pass with flipped weights, scale = 1, shift = 0).
+extern "C" int adn_conv3x3_affine_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
+                                       const void* w_packed, int c_out, const float* scale, const float* shift, int relu, void* out,
+                                       void* stream) {
+    return adn::conv3x3_halo(src0, c0, src1, c1, h1, w1, n, h, w, w_packed, c_out, scale, shift, adn::HEPI_NHWC, out, nullptr,
+                             nullptr, nullptr, nullptr, (cudaStream_t)stream, relu);
 }
 
 extern "C" int adn_conv3x3_bn_relu_head_f32(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,

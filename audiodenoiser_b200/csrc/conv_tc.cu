@@ -36,11 +36,16 @@ struct ConvTArgs {
     int n_img, H, W;               // input pixel grid
     int tiles_x, tiles_y, tw_log2; // pixel tile = TH x TW, TW = 1 << tw_log2, TH = 128 >> tw_log2
     int c_out, n_blocks, num_tiles;
-    const float* bias;             // [c_out]
+    const float* bias;             // [c_out] (forward) or NULL
+    int dgrad;                     // 0: forward ConvTranspose2d (one A map, four pixel-shuffle output maps)
+                                   // 1: its data gradient (four quadrant A maps over d_out, K = 4*Cout, one dense output map)
+    int a_chunks_per_map;          // dgrad: Cout / 64 chunks per quadrant
+    int n_valid;                   // dgrad: valid GEMM columns (= Cin); the 256-wide N block may overhang
 };
 
 __global__ void __launch_bounds__(CONV_THREADS, 1)
-convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmA3, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
                   const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3, const ConvTArgs a) {
     extern __shared__ uint8_t smem_dyn[];
@@ -61,7 +66,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmA3);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmO0); tma_prefetch_desc(&tmO1); tma_prefetch_desc(&tmO2); tma_prefetch_desc(&tmO3);
     }
@@ -96,7 +101,13 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * T_STAGE_BYTES;
                     mbar_arrive_expect_tx(full_bar(stage), T_STAGE_BYTES);
-                    tma_load_4d(sa, &tmA, full_bar(stage), ch * BLOCK_K, tx * TW, ty * TH, img);
+                    if (!a.dgrad) {
+                        tma_load_4d(sa, &tmA, full_bar(stage), ch * BLOCK_K, tx * TW, ty * TH, img);
+                    } else {                                         // K chunk = (quadrant q, 64-channel block) of d_out
+                        const int q = ch / a.a_chunks_per_map, cc = ch - q * a.a_chunks_per_map;
+                        const CUtensorMap* ma = (q == 0) ? &tmA : (q == 1) ? &tmA1 : (q == 2) ? &tmA2 : &tmA3;
+                        tma_load_4d(sa, ma, full_bar(stage), cc * BLOCK_K, tx * TW, ty * TH, img);
+                    }
                     tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), ch * BLOCK_K, n_blk * T_BLOCK_N);
                     if (++stage == T_STAGES) { stage = 0; phase ^= 1u; }
                 }
@@ -135,7 +146,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;                            // accumulator row = input pixel within the tile
         const int et = threadIdx.x - 64;                             // 0..127
-        for (int c = et; c < a.c_out; c += EPI_THREADS) s_bias[c] = a.bias[c];
+        if (a.bias) for (int c = et; c < a.c_out; c += EPI_THREADS) s_bias[c] = a.bias[c];
         named_bar_sync(1, EPI_THREADS);
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
@@ -152,7 +163,9 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll 1
             for (int g = 0; g < T_BLOCK_N / 64; ++g) {               // one 64-column group = one (quadrant, 64-channel) store
                 const int n = n_blk * T_BLOCK_N + g * 64;
-                const int q = n / a.c_out, co = n - q * a.c_out;     // a group never straddles a quadrant (c_out % 64 == 0)
+                if (a.dgrad && n >= a.n_valid) break;                // uniform: the N block overhangs Cin
+                const int q = a.dgrad ? 0 : n / a.c_out;             // a group never straddles a quadrant (c_out % 64 == 0)
+                const int co = n - q * a.c_out;
                 const uint32_t o_stage = out_stage_base + (store_groups & 1u) * T_OUT_STAGE;
                 if (et == 0) bulk_wait_read<1>();                    // the store that last used this buffer has read it
                 named_bar_sync(1, EPI_THREADS);
@@ -163,13 +176,15 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     tmem_ld32(t_row + (uint32_t)(g * 64 + half * 32), r);
                     tmem_ld_wait();
                     const float* bias = s_bias + co + half * 32;
+                    const bool has_bias = a.bias != nullptr;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         uint32_t w[4];
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * j]) + bias[8 * i + 2 * j],
-                                                                      __uint_as_float(r[8 * i + 2 * j + 1]) + bias[8 * i + 2 * j + 1]);
+                            const float b0 = has_bias ? bias[8 * i + 2 * j] : 0.f, b1 = has_bias ? bias[8 * i + 2 * j + 1] : 0.f;
+                            __nv_bfloat162 p = __floats2bfloat162_rn(__uint_as_float(r[8 * i + 2 * j]) + b0,
+                                                                      __uint_as_float(r[8 * i + 2 * j + 1]) + b1);
                             w[j] = *reinterpret_cast<uint32_t*>(&p);
                         }
                         st_shared_v4(rbase + ((((uint32_t)(half * 4 + i)) ^ ((uint32_t)row & 7u)) << 4), w[0], w[1], w[2], w[3]);
@@ -236,6 +251,7 @@ static int convt_gemm(const void* src, int c_in, int n, int h, int w, const void
     if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
     args.num_tiles = (int)tiles;
     args.bias = bias;
+    args.dgrad = 0; args.a_chunks_per_map = args.k_chunks; args.n_valid = n_total;
 
     CUtensorMap mA, mB, mO[4];
     st = make_act_map(&mA, src, n, h, w, c_in, tw, th);
@@ -251,12 +267,73 @@ static int convt_gemm(const void* src, int c_in, int n, int h, int w, const void
     ADN_CUDA_TRY(ensure_dyn_smem(convt_gemm_kernel, T_SMEM_BYTES, smem_set));
     const int sms = num_sms();
     const int grid = args.num_tiles < sms ? args.num_tiles : sms;
-    convt_gemm_kernel<<<grid, CONV_THREADS, T_SMEM_BYTES, stream>>>(mA, mB, mO[0], mO[1], mO[2], mO[3], args);
+    convt_gemm_kernel<<<grid, CONV_THREADS, T_SMEM_BYTES, stream>>>(mA, mA, mA, mA, mB, mO[0], mO[1], mO[2], mO[3], args);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+// quadrant (dy, dx) of a channel slice [c_off, c_off + c) of an (n, 2h, 2w, ld) tensor, as an (n, h, w, c) view
+static int make_quadrant_view(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int ld, int c_off, int dy, int dx, int tw, int th) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) return ADN_ERR_DRIVER;
+    const char* base = static_cast<const char*>(ptr) + (((size_t)dy * (2 * w) + dx) * ld + c_off) * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)2 * ld * 2, (cuuint64_t)2 * (2 * w) * ld * 2, (cuuint64_t)(2 * h) * (2 * w) * ld * 2};
+    cuuint32_t box[4] = {64u, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
+}
+
+// data gradient of ConvTranspose2d(k=2,s=2): d_in[p][ci] = sum_{q,co} d_out[2p+q][co] * W[ci][co][q]
+//   GEMM: M = n*h*w input pixels, K = 4*Cout (chunk = quadrant x 64 channels, A boxes from the quadrant views of d_out),
+//   N = Cin, B = weights packed [ci][q*Cout + co] bf16 (adn_pack_convt2x2_dgrad_weight_bf16).
+static int convt_dgrad(const void* d_out, int out_ld, int out_off, int c_out, int n, int h, int w, const void* w_packed, int c_in, void* d_in,
+                       cudaStream_t stream) {
+    if (!d_out || !w_packed || !d_in || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
+    if (c_in <= 0 || (c_in % 64) || c_out <= 0 || (c_out % 64) || out_off < 0 || out_off + c_out > out_ld || (out_ld % 8) || (out_off % 8)) return ADN_ERR_ARG;
+    if (!aligned16(d_out) || !aligned16(w_packed) || !aligned16(d_in)) return ADN_ERR_ARG;
+    int st = check_device();
+    if (st != ADN_OK) return st;
+    auto padded = [&](int th, int tw) { return (long long)((h + th - 1) / th) * th * ((w + tw - 1) / tw) * tw; };
+    const int tw_log2 = padded(8, 16) <= padded(16, 8) ? 4 : 3;
+    const int tw = 1 << tw_log2, th = BLOCK_M >> tw_log2;
+    ConvTArgs args;
+    args.k_chunks = 4 * (c_out / 64);
+    args.n_img = n; args.H = h; args.W = w;
+    args.tiles_x = (w + tw - 1) / tw; args.tiles_y = (h + th - 1) / th; args.tw_log2 = tw_log2;
+    args.c_out = c_in;                                          // epilogue column -> channel of the single output map
+    args.n_blocks = (c_in + T_BLOCK_N - 1) / T_BLOCK_N;
+    const long long tiles = (long long)n * args.tiles_x * args.tiles_y * args.n_blocks;
+    if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
+    args.num_tiles = (int)tiles;
+    args.bias = nullptr;
+    args.dgrad = 1; args.a_chunks_per_map = c_out / 64; args.n_valid = c_in;
+    CUtensorMap mA[4], mB, mO;
+    for (int q = 0; q < 4; ++q) {
+        st = make_quadrant_view(&mA[q], d_out, n, h, w, c_out, out_ld, out_off, q >> 1, q & 1, tw, th);
+        if (st != ADN_OK) return st;
+    }
+    st = make_weight_map(&mB, w_packed, c_in, 4 * c_out, T_BLOCK_N);
+    if (st != ADN_OK) return st;
+    st = make_act_map(&mO, d_in, n, h, w, c_in, tw, th);
+    if (st != ADN_OK) return st;
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(convt_gemm_kernel, T_SMEM_BYTES, smem_set));
+    const int sms = num_sms();
+    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    convt_gemm_kernel<<<grid, CONV_THREADS, T_SMEM_BYTES, stream>>>(mA[0], mA[1], mA[2], mA[3], mB, mO, mO, mO, mO, args);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
 
 }  // namespace adn
+
+extern "C" int adn_convt2x2_dgrad_bf16(const void* d_out, int out_ld, int out_off, int c_out, int n, int h, int w, const void* w_packed,
+                                       int c_in, void* d_in, void* stream) {
+    return adn::convt_dgrad(d_out, out_ld, out_off, c_out, n, h, w, w_packed, c_in, d_in, (cudaStream_t)stream);
+}
 
 extern "C" int adn_convt2x2_bf16(const void* src, int c_in, int n, int h, int w, const void* w_packed, int c_out, const float* bias,
                                  void* out, void* stream) {

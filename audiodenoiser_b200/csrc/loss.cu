@@ -194,6 +194,176 @@ __global__ void loss_finalize_kernel(const double* __restrict__ sums, const doub
     out4[3] = (float)l1m;
 }
 
+// ------------------------------------------------------------------------------------------------ backward
+// d(c_stft * stft + c_mel * mel + c_l1 * l1) / d pred.  Both spectral terms depend on pred only through the envelope
+// e[b][t] = mean_f pred[b][f][t], so the kernel below produces dE (B, T) and the elementwise pass adds dE / F to the L1 term.
+//   phase 1 (per transform): the forward DFT again, storing for every (frame, bin) the cotangent of (re, im):
+//        rectangular scales: sign(|P| - |T|) * (re, im) / |P| * c_stft / (3 B bins frames)       (d|z| = 0 at z = 0, like torch)
+//        mel:                2 (re, im) * sum_m sign(mel_p - mel_t)[m] fb[k][m] * c_mel / (B 64 frames)
+//   phase 2: every envelope sample GATHERS its contributions (frames covering it x bins) in a fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+loss_backward_env_kernel(const float* __restrict__ env, int T, int B, const float* __restrict__ mel_fb, float c_stft, float c_mel,
+                         float* __restrict__ scratch, long long scratch_per_sample, float* __restrict__ d_env) {
+    extern __shared__ float smem[];
+    float* xp = smem;                       // [T]
+    float* xt = xp + T;                     // [T]
+    float* de = xt + T;                     // [T]
+    float* tw_c = de + T;                   // [64]
+    float* tw_s = tw_c + 64;                // [64]
+    float* win = tw_s + 64;                 // [64]
+    float* fb = win + 64;                   // [32][64]
+    float* msgn = fb + MEL_BINS * MEL_N;    // [8 frames][64 mels] sign(mel_p - mel_t)
+    float* pw = msgn + 8 * MEL_N;           // [2][8][32]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float* G = scratch + (long long)b * scratch_per_sample;
+    for (int i = tid; i < T; i += blockDim.x) { xp[i] = env[((size_t)b * 2) * T + i]; xt[i] = env[((size_t)b * 2 + 1) * T + i]; de[i] = 0.f; }
+    for (int i = tid; i < MEL_BINS * MEL_N; i += blockDim.x) fb[i] = mel_fb[i];
+    if (tid < 64) win[tid] = tid < MEL_NFFT ? 0.5f - 0.5f * cospif(2.0f * (float)tid / (float)MEL_NFFT) : 0.f;
+
+    const int nffts[3] = {63, 32, 16}, hops[3] = {16, 8, 4};
+    for (int s = 0; s < 3; ++s) {
+        const int n = nffts[s], hop = hops[s], pad = n / 2, bins = n / 2 + 1;
+        const int frames = 1 + (T + 2 * pad - n) / hop;
+        const float coef = c_stft / (3.0f * (float)B * (float)bins * (float)frames);
+        __syncthreads();
+        if (tid < n) sincospif(2.0f * (float)tid / (float)n, &tw_s[tid], &tw_c[tid]);
+        __syncthreads();
+        for (int item = tid; item < frames * bins; item += blockDim.x) {
+            const int fr = item / bins, k = item - fr * bins;
+            const int start = fr * hop - pad;
+            float pr = 0.f, pi = 0.f, tr = 0.f, ti = 0.f;
+            int m = 0;
+            for (int i = 0; i < n; ++i) {
+                const int idx = start + i;
+                if (idx >= 0 && idx < T) {
+                    const float c = tw_c[m], sn = tw_s[m];
+                    const float a = xp[idx], g = xt[idx];
+                    pr = fmaf(a, c, pr); pi = fmaf(a, sn, pi);
+                    tr = fmaf(g, c, tr); ti = fmaf(g, sn, ti);
+                }
+                m += k; if (m >= n) m -= n;
+            }
+            const float mp = sqrtf(pr * pr + pi * pi), mt = sqrtf(tr * tr + ti * ti);
+            const float sg = (mp > mt) ? 1.f : (mp < mt) ? -1.f : 0.f;
+            const float w = mp > 0.f ? coef * sg / mp : 0.f;
+            G[2 * item] = w * pr;
+            G[2 * item + 1] = w * pi;
+        }
+        __syncthreads();
+        for (int j = tid; j < T; j += blockDim.x) {
+            // frames with start <= j < start + n, start = fr*hop - pad
+            const int fr_lo = max(0, (j + pad - n + hop) / hop), fr_hi = min(frames - 1, (j + pad) / hop);
+            float acc = 0.f;
+            for (int fr = fr_lo; fr <= fr_hi; ++fr) {
+                const int i = j - (fr * hop - pad);
+                if (i < 0 || i >= n) continue;
+                int m = 0;
+                for (int k = 0; k < bins; ++k) {
+                    acc = fmaf(G[2 * (fr * bins + k)], tw_c[m], acc);
+                    acc = fmaf(G[2 * (fr * bins + k) + 1], tw_s[m], acc);
+                    m += i; if (m >= n) m -= n;
+                }
+            }
+            de[j] += acc;
+        }
+        __syncthreads();
+    }
+    {   // mel term
+        const int pad = MEL_NFFT / 2;
+        const int frames = 1 + (T + 2 * pad - MEL_NFFT) / MEL_HOP;
+        const float coef = c_mel / ((float)B * (float)MEL_N * (float)frames);
+        __syncthreads();
+        if (tid < MEL_NFFT) sincospif(2.0f * (float)tid / (float)MEL_NFFT, &tw_s[tid], &tw_c[tid]);
+        __syncthreads();
+        for (int f0 = 0; f0 < frames; f0 += 8) {
+            const int nf = min(8, frames - f0);
+            for (int item = tid; item < 2 * nf * MEL_BINS; item += blockDim.x) {
+                const int sig = item / (nf * MEL_BINS);
+                const int rem = item - sig * nf * MEL_BINS;
+                const int fr = rem / MEL_BINS, k = rem - fr * MEL_BINS;
+                const float* x = sig ? xt : xp;
+                const int start = (f0 + fr) * MEL_HOP - pad;
+                float re = 0.f, im = 0.f;
+                int m = 0;
+                for (int i = 0; i < MEL_NFFT; ++i) {
+                    int idx = start + i;
+                    if (idx < 0) idx = -idx;
+                    if (idx >= T) idx = 2 * (T - 1) - idx;
+                    const float v = x[idx] * win[i];
+                    re = fmaf(v, tw_c[m], re); im = fmaf(v, tw_s[m], im);
+                    m += k; if (m >= MEL_NFFT) m -= MEL_NFFT;
+                }
+                pw[(sig * 8 + fr) * MEL_BINS + k] = re * re + im * im;
+                if (sig == 0) { G[2 * ((f0 + fr) * MEL_BINS + k)] = re; G[2 * ((f0 + fr) * MEL_BINS + k) + 1] = im; }
+            }
+            __syncthreads();
+            for (int item = tid; item < nf * MEL_N; item += blockDim.x) {
+                const int fr = item / MEL_N, mel = item - fr * MEL_N;
+                float mp = 0.f, mt = 0.f;
+#pragma unroll 8
+                for (int k = 0; k < MEL_BINS; ++k) {
+                    const float w = fb[k * MEL_N + mel];
+                    mp = fmaf(pw[fr * MEL_BINS + k], w, mp);
+                    mt = fmaf(pw[(8 + fr) * MEL_BINS + k], w, mt);
+                }
+                msgn[fr * MEL_N + mel] = (mp > mt) ? 1.f : (mp < mt) ? -1.f : 0.f;
+            }
+            __syncthreads();
+            for (int item = tid; item < nf * MEL_BINS; item += blockDim.x) {        // cotangent of (re, im) of the pred spectrum
+                const int fr = item / MEL_BINS, k = item - fr * MEL_BINS;
+                float g = 0.f;
+#pragma unroll 8
+                for (int mel = 0; mel < MEL_N; ++mel) g = fmaf(msgn[fr * MEL_N + mel], fb[k * MEL_N + mel], g);
+                g *= 2.f * coef;
+                G[2 * ((f0 + fr) * MEL_BINS + k)] *= g;
+                G[2 * ((f0 + fr) * MEL_BINS + k) + 1] *= g;
+            }
+            __syncthreads();
+        }
+        for (int j = tid; j < T; j += blockDim.x) {
+            // padded positions that reflect onto j: q = j, q = -j (j >= 1), q = 2(T-1) - j (j <= T-2)
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                int q;
+                if (c == 0) q = j;
+                else if (c == 1) { if (j < 1) continue; q = -j; }
+                else { if (j > T - 2) continue; q = 2 * (T - 1) - j; }
+                if (q < -pad || q > T - 1 + pad) continue;
+                const int fr_lo = max(0, (q + pad - MEL_NFFT + MEL_HOP) / MEL_HOP), fr_hi = min(frames - 1, (q + pad) / MEL_HOP);
+                for (int fr = fr_lo; fr <= fr_hi; ++fr) {
+                    const int i = q - (fr * MEL_HOP - pad);
+                    if (i < 0 || i >= MEL_NFFT) continue;
+                    float a2 = 0.f;
+                    int m = 0;
+                    for (int k = 0; k < MEL_BINS; ++k) {
+                        a2 = fmaf(G[2 * (fr * MEL_BINS + k)], tw_c[m], a2);
+                        a2 = fmaf(G[2 * (fr * MEL_BINS + k) + 1], tw_s[m], a2);
+                        m += i; if (m >= MEL_NFFT) m -= MEL_NFFT;
+                    }
+                    acc = fmaf(a2, win[i], acc);
+                }
+            }
+            de[j] += acc;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < T; i += blockDim.x) d_env[(size_t)b * T + i] = de[i];
+}
+
+// d_pred[b][f][t] = c_l1 * sign(pred - target) / (B F T) + d_env[b][t] / F
+__global__ void __launch_bounds__(256)
+loss_backward_apply_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ d_env, int F, int T,
+                           long long total, float c_l1_over_n, float inv_f, float* __restrict__ d_pred) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % T);
+        const long long b = i / ((long long)F * T);
+        const float d = __ldcs(pred + i) - __ldcs(target + i);
+        const float sg = (d > 0.f) ? 1.f : (d < 0.f) ? -1.f : 0.f;
+        d_pred[i] = fmaf(sg, c_l1_over_n, d_env[b * T + t] * inv_f);
+    }
+}
+
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace adn
@@ -229,6 +399,54 @@ extern "C" int adn_combined_loss_f32(const float* pred, const float* target, int
     loss_spectral_kernel<<<(unsigned)batch, 256, smem, s>>>(env, frames, mel_fb_32x64, sums);
     ADN_LAUNCH_CHECK();
     loss_finalize_kernel<<<1, 32, 0, s>>>(sums, l1p, (int)(batch * tx), (int)batch, freq, frames, out4);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+static inline long long loss_bwd_scratch_floats(int T) {
+    long long f63 = 1 + (T - 1) / 16, f32 = 1 + T / 8, f16 = 1 + T / 4;
+    long long m = f63 * 32;
+    if (f32 * 17 > m) m = f32 * 17;
+    if (f16 * 9 > m) m = f16 * 9;
+    return 2 * m + 16;
+}
+
+extern "C" int64_t adn_loss_backward_workspace_bytes(int64_t batch, int freq, int frames) {
+    if (batch < 0 || freq <= 0 || frames <= 0) return -1;
+    return (int64_t)(align256((size_t)batch * 2 * frames * sizeof(float)) + align256((size_t)batch * frames * sizeof(float)) +
+                     align256((size_t)batch * loss_bwd_scratch_floats(frames) * sizeof(float)) +
+                     align256((size_t)batch * ((frames + ENV_TX - 1) / ENV_TX) * sizeof(double)));
+}
+
+// Gradient of c_stft * stft + c_mel * mel + c_l1 * l1 (the three terms of CombinedPerceptualLoss, loss.py:83-95) with respect
+// to pred; loss.backward() at train.py:69 is (c_stft, c_mel, c_l1) = (0.4, 0.4, 0.2).  d_pred: (batch,1,freq,frames) float32.
+extern "C" int adn_combined_loss_backward_f32(const float* pred, const float* target, int64_t batch, int freq, int frames,
+                                              const float* mel_fb_32x64, float c_stft, float c_mel, float c_l1, void* workspace,
+                                              float* d_pred, void* stream) {
+    if (batch <= 0 || freq <= 0 || frames <= 0) return ADN_ERR_ARG;
+    if (!pred || !target || !mel_fb_32x64 || !workspace || !d_pred) return ADN_ERR_ARG;
+    if (frames > LOSS_MAX_T / 2 || frames <= MEL_NFFT / 2 || batch > 65535) return ADN_ERR_ARG;
+    int st = check_device();
+    if (st != ADN_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    char* ws = static_cast<char*>(workspace);
+    float* env = reinterpret_cast<float*>(ws); ws += align256((size_t)batch * 2 * frames * sizeof(float));
+    float* d_env = reinterpret_cast<float*>(ws); ws += align256((size_t)batch * frames * sizeof(float));
+    float* scratch = reinterpret_cast<float*>(ws); ws += align256((size_t)batch * loss_bwd_scratch_floats(frames) * sizeof(float));
+    double* l1p = reinterpret_cast<double*>(ws);
+    const int tx = (frames + ENV_TX - 1) / ENV_TX;
+    loss_envelope_kernel<<<dim3(tx, (unsigned)batch), dim3(ENV_TX, ENV_FY), 0, s>>>(pred, target, freq, frames, env, l1p);
+    ADN_LAUNCH_CHECK();
+    const size_t smem = (size_t)(3 * frames + 3 * 64 + MEL_BINS * MEL_N + 8 * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float);
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(loss_backward_env_kernel, (int)((3 * (LOSS_MAX_T / 2) + 3 * 64 + MEL_BINS * MEL_N + 8 * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float)), smem_set));
+    loss_backward_env_kernel<<<(unsigned)batch, 256, smem, s>>>(env, frames, (int)batch, mel_fb_32x64, c_stft, c_mel, scratch,
+                                                               loss_bwd_scratch_floats(frames), d_env);
+    ADN_LAUNCH_CHECK();
+    const long long total = (long long)batch * freq * frames;
+    long long g = (total + 255) / 256; const long long cap = (long long)num_sms() * 16; if (g > cap) g = cap;
+    loss_backward_apply_kernel<<<(int)g, 256, 0, s>>>(pred, target, d_env, freq, frames, total, c_l1 / (float)((double)batch * freq * frames),
+                                                     1.0f / (float)freq, d_pred);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

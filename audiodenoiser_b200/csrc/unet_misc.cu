@@ -31,6 +31,28 @@ __global__ void pack_convt2x2_kernel(const float* __restrict__ w, int ci_n, int 
     }
 }
 
+// data-gradient weights of Conv2d 3x3: Wd[ci][tap'][co] = W[co][ci][2-ky][2-kx] (flipped taps, transposed channels), so that
+// d_in = conv3x3(d_out, Wd) runs on the forward kernel
+__global__ void pack_conv3x3_dgrad_kernel(const float* __restrict__ w, int co_n, int ci_n, __nv_bfloat16* __restrict__ out) {
+    const long long total = (long long)ci_n * 9 * co_n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % co_n);
+        const int tap = (int)((i / co_n) % 9);
+        const int ci = (int)(i / ((long long)co_n * 9));
+        out[i] = __float2bfloat16_rn(w[((long long)co * ci_n + ci) * 9 + (8 - tap)]);
+    }
+}
+// data-gradient weights of ConvTranspose2d 2x2: Wd[ci][q * Co + co] = W[ci][co][q]
+__global__ void pack_convt2x2_dgrad_kernel(const float* __restrict__ w, int ci_n, int co_n, __nv_bfloat16* __restrict__ out) {
+    const long long total = 4ll * co_n * ci_n;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % co_n);
+        const int q = (int)((i / co_n) % 4);
+        const int ci = (int)(i / (4ll * co_n));
+        out[i] = __float2bfloat16_rn(w[((long long)ci * co_n + co) * 4 + q]);
+    }
+}
+
 __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
                                float* __restrict__ scale, float* __restrict__ shift) {
@@ -50,7 +72,7 @@ __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float*
 constexpr int C1_RUN = 4;
 __global__ void __launch_bounds__(256)
 conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float* __restrict__ weight,
-                  const float* __restrict__ scale, const float* __restrict__ shift, uint4* __restrict__ out) {
+                  const float* __restrict__ scale, const float* __restrict__ shift, float relu_floor, uint4* __restrict__ out) {
     __shared__ __align__(16) float s_w[9][64];
     for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w[i % 9][i / 9] = weight[i];   // weight[c][tap]
     const int cg = threadIdx.x & 7, grp = threadIdx.x >> 3;
@@ -95,7 +117,7 @@ conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float*
                 if (px0 + r < w) {
                     float y[8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[r][c], sc[c], sh[c]), 0.f);
+                    for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[r][c], sc[c], sh[c]), relu_floor);
                     uint4 o;
                     o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
                     o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
@@ -226,6 +248,22 @@ extern "C" int adn_pack_convt2x2_weight_bf16(const float* w, int c_in, int c_out
     return ADN_OK;
 }
 
+extern "C" int adn_pack_conv3x3_dgrad_weight_bf16(const float* w, int c_out, int c_in, void* packed, void* stream) {
+    if (!w || !packed || c_out <= 0 || c_in <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    pack_conv3x3_dgrad_kernel<<<grid_for((long long)c_out * 9 * c_in), 256, 0, (cudaStream_t)stream>>>(w, c_out, c_in, (__nv_bfloat16*)packed);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int c_out, void* packed, void* stream) {
+    if (!w || !packed || c_out <= 0 || c_in <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    pack_convt2x2_dgrad_kernel<<<grid_for(4ll * c_out * c_in), 256, 0, (cudaStream_t)stream>>>(w, c_in, c_out, (__nv_bfloat16*)packed);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
 extern "C" int adn_fold_bn_f32(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,
                                float eps, int channels, float* scale, float* shift, void* stream) {
     if (!gamma || !beta || !mean || !var || !scale || !shift || channels <= 0) return ADN_ERR_ARG;
@@ -239,7 +277,18 @@ extern "C" int adn_conv3x3_c1_bn_relu_bf16(const float* x, int n, int h, int w, 
                                            const float* shift, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, (uint4*)out);
+    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, 0.f, (uint4*)out);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+// first layer without the activation (train-mode pre-BatchNorm output: scale = 1, shift = conv bias)
+extern "C" int adn_conv3x3_c1_affine_bf16(const float* x, int n, int h, int w, const float* weight, const float* scale,
+                                          const float* shift, int relu, void* out, void* stream) {
+    if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+        x, n, h, w, weight, scale, shift, relu ? 0.f : -INFINITY, (uint4*)out);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

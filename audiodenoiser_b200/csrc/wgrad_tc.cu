@@ -1,0 +1,275 @@
+// wgrad_tc.cu -- weight gradients of Conv2d 3x3 and ConvTranspose2d 2x2 (the backward of code/model.py:11,14,38 driven by
+// loss.backward() at code/train.py:69) as a tcgen05/TMEM GEMM that CONTRACTS OVER PIXELS, for sm_100a.
+//
+//   GEMM view    D_tap[m, n] += sum_px A[px, m] * B_tap[px, n]        (bf16 x bf16 -> fp32 in TMEM)
+//                Conv3x3:   A = dz (gradient of the conv output, m = co), B_tap = the conv input shifted by the tap
+//                           (n = ci), three taps (one kernel row ky) per CTA:   dW[co][ci][ky][kx] = D_kx[co][ci];
+//                ConvT 2x2: A = the convT input (m = ci), B_q = quadrant q of the output gradient (n = co), four taps:
+//                           dW[ci][co][dy][dx] = D_q[ci][co].
+//   operands     both are NHWC activations, so the contraction index (pixel) is the SLOW index of the shared-memory tile and
+//                the M / N index (channel) is contiguous: MN-major UMMA operands (instruction-descriptor bits 15/16).  A k-step
+//                is an 8x8 pixel tile = 64 rows of 128 B; one 4-D TMA box {64 ch, 8, 8, 1} per 64-channel block lands as
+//                MN-major SWIZZLE_128B atoms (8 pixel rows x 64 channels = 1024 B): SBO = 1024 B between 8-pixel groups,
+//                LBO = 8192 B between 64-channel blocks.  Tap shifts are TMA coordinates; out-of-image pixels arrive as zeros
+//                (= the conv's zero padding).
+//   split-K      the pixel range is split across CTAs; partial results are added into the fp32 gradient buffer with
+//                red.global.add (the buffer is zeroed by the optimizer's zero_grad, train.py:66).
+//   roles        warp 0: TMA producer - warp 1: tcgen05.mma issuer - warps 2..5: epilogue (tcgen05.ld -> red.add).
+#include "tc_common.cuh"
+
+namespace adn {
+
+constexpr int WG_SUB = 64 * 128;               // one [64 px][64 ch] bf16 sub-tile
+constexpr int WG_THREADS = 192;
+constexpr int WG_MAX_STAGES = 6;
+constexpr int WG_MAX_TAPS = 4;
+
+struct WgradArgs {
+    int tiles_x, tiles_y, kt_total;            // 8x8 pixel tiling of the (n, h, w) grid
+    int m_blocks, n_blocks, splits;            // blockIdx.x = (mb * n_blocks + nb) * splits + s
+    int taps, stages;
+    int tap_dy[WG_MAX_TAPS], tap_dx[WG_MAX_TAPS], tap_map[WG_MAX_TAPS];
+    long long tap_off[WG_MAX_TAPS];            // output element offset of each tap
+    int m_total, n_total;
+    long long sm, sn;                          // output strides in elements
+    float* out;
+    uint32_t lbo, sbo;                         // MN-major descriptor strides (bytes)
+};
+
+__device__ __forceinline__ uint64_t make_mn_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_mn(int n) { return make_idesc(n) | (1u << 15) | (1u << 16); }
+
+template <int BN>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmB3, const WgradArgs a) {
+    constexpr int NSUB = BN / 64;
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const uint32_t stage_bytes = (uint32_t)(2 + a.taps * NSUB) * WG_SUB;
+    const uint32_t aux_off = (uint32_t)a.stages * stage_bytes;
+    const uint32_t bar_base = smem_base + aux_off;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (WG_MAX_STAGES + s); };
+    const uint32_t tfull = bar_base + 8u * (2 * WG_MAX_STAGES);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + aux_off + (2 * WG_MAX_STAGES + 1) * 8);
+    constexpr int TMEM_COLS = (WG_MAX_TAPS * BN) < 32 ? 32 : WG_MAX_TAPS * BN;      // 256 or 512
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmB3);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < WG_MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) { tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int s_idx = blockIdx.x % a.splits;
+    const int mn = blockIdx.x / a.splits;
+    const int nb = mn % a.n_blocks, mb = mn / a.n_blocks;
+    const int per = (a.kt_total + a.splits - 1) / a.splits;
+    const int kt0 = s_idx * per, kt1 = min(a.kt_total, kt0 + per);
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kt = kt0; kt < kt1; ++kt) {
+                const int img = kt / tiles_per_img;
+                const int rem = kt - img * tiles_per_img;
+                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+                const int x0 = tx * 8, y0 = ty * 8;
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+                const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+                tma_load_4d(sa, &tmA, full_bar(stage), mb * 128, x0, y0, img);
+                tma_load_4d(sa + WG_SUB, &tmA, full_bar(stage), mb * 128 + 64, x0, y0, img);
+                for (int t = 0; t < a.taps; ++t) {
+                    const CUtensorMap* mp = (a.tap_map[t] == 0) ? &tmB0 : (a.tap_map[t] == 1) ? &tmB1 : (a.tap_map[t] == 2) ? &tmB2 : &tmB3;
+                    for (int j = 0; j < NSUB; ++j)
+                        tma_load_4d(sa + (uint32_t)(2 + t * NSUB + j) * WG_SUB, mp, full_bar(stage), nb * BN + j * 64, x0 + a.tap_dx[t],
+                                    y0 + a.tap_dy[t], img);
+                }
+                if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_mn(BN);
+        int stage = 0; uint32_t phase = 0;
+        for (int kt = kt0; kt < kt1; ++kt) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
+            if (elect_one()) {
+                for (int t = 0; t < a.taps; ++t) {
+                    const uint32_t sb = sa + (uint32_t)(2 + t * NSUB) * WG_SUB;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)              // UMMA_K = 16 pixels = 16 rows of 128 B
+                        umma_bf16(tmem_base + (uint32_t)(t * BN), make_mn_sw128_desc(sa + k * 2048, a.lbo, a.sbo),
+                                  make_mn_sw128_desc(sb + k * 2048, a.lbo, a.sbo), idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(empty_bar(stage));
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (elect_one()) umma_commit(tfull);
+        __syncwarp();
+    } else if (kt1 > kt0) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int m = mb * 128 + row;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+        for (int t = 0; t < a.taps; ++t) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * BN + c0), r);
+                tmem_ld_wait();
+                if (m < a.m_total) {
+                    float* o = a.out + (long long)m * a.sm + a.tap_off[t] + (long long)(nb * BN + c0) * a.sn;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (nb * BN + c0 + i < a.n_total) atomicAdd(o + (long long)i * a.sn, __uint_as_float(r[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// debug hook (not part of the public header): MN-major descriptor strides
+static uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024;
+
+// a channel slice [c_off, c_off + c) of an NHWC tensor whose pixels are `ld` channels apart, sampled on the (h, w) grid with
+// pixel steps (sy, sx) starting at (oy, ox): element (ch, x, y, img) = base[((img * H_full + oy + sy*y) * W_full + ox + sx*x) * ld + c_off + ch]
+static int make_view_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int c, int ld, int c_off, int h_full, int w_full,
+                         int sy, int sx, int oy, int ox) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) return ADN_ERR_DRIVER;
+    const char* base = static_cast<const char*>(ptr) + (((size_t)oy * w_full + ox) * ld + c_off) * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)sx * ld * 2, (cuuint64_t)sy * w_full * ld * 2, (cuuint64_t)h_full * w_full * ld * 2};
+    cuuint32_t box[4] = {64u, 8u, 8u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
+}
+
+static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs& args, int n, int h, int w, cudaStream_t stream) {
+    args.tiles_x = (w + 7) / 8; args.tiles_y = (h + 7) / 8;
+    const long long kt = (long long)n * args.tiles_x * args.tiles_y;
+    if (kt > 0x7fffffffLL) return ADN_ERR_ARG;
+    args.kt_total = (int)kt;
+    const int bn = (args.n_total % 128 == 0) ? 128 : 64;
+    args.m_blocks = (args.m_total + 127) / 128;
+    args.n_blocks = (args.n_total + bn - 1) / bn;
+    const int mn = args.m_blocks * args.n_blocks;
+    int splits = (2 * num_sms() + mn - 1) / mn;
+    if (splits > args.kt_total) splits = args.kt_total;
+    if (splits < 1) splits = 1;
+    // every split must own at least one k-step: shrink until ceil(kt / splits) * (splits - 1) < kt
+    while (splits > 1 && (long long)((args.kt_total + splits - 1) / splits) * (splits - 1) >= args.kt_total) --splits;
+    args.splits = splits;
+    args.lbo = g_wg_lbo; args.sbo = g_wg_sbo;
+    const int stage_bytes = (2 + args.taps * (bn / 64)) * WG_SUB;
+    int stages = (225 * 1024 - 2048) / stage_bytes;
+    if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
+    if (stages < 2) return ADN_ERR_ARG;
+    args.stages = stages;
+    const int smem = 1024 + stages * stage_bytes + (2 * WG_MAX_STAGES + 1) * 8 + 16;
+    const int grid = mn * splits;
+    if (bn == 128) {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(wgrad_kernel<128>, 232448, smem_set));
+        wgrad_kernel<128><<<grid, WG_THREADS, smem, stream>>>(mA, mB[0], mB[1], mB[2], mB[3], args);
+    } else {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(wgrad_kernel<64>, 232448, smem_set));
+        wgrad_kernel<64><<<grid, WG_THREADS, smem, stream>>>(mA, mB[0], mB[1], mB[2], mB[3], args);
+    }
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+}  // namespace adn
+
+using namespace adn;
+
+extern "C" void adn__wgrad_set_desc(int lbo_bytes, int sbo_bytes) { g_wg_lbo = (uint32_t)lbo_bytes; g_wg_sbo = (uint32_t)sbo_bytes; }
+
+// d_weight[(co * ci_total + ci_off + ci) * 9 + ky * 3 + kx] += sum_p dz[p][co] * x[p + (ky-1, kx-1)][ci]   (reference layout
+// (Co, Ci, 3, 3) of model.py:11,14).  dz: (n,h,w,c_out) dense; x: (n,h1,w1,c_in) dense, (h1,w1) <= (h,w) (a zero-padded
+// up-sampled map, model.py:44-47).  ci_off / ci_total address the slice of a concatenated input (model.py:49).
+extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, int c_in, int h1, int w1, int n, int h, int w,
+                                     float* d_weight, int ci_off, int ci_total, void* stream) {
+    if (!dz || !x || !d_weight || n <= 0 || h <= 0 || w <= 0 || c_out <= 0 || (c_out % 64) || c_in <= 0 || (c_in % 64)) return ADN_ERR_ARG;
+    if (h1 <= 0 || w1 <= 0 || h1 > h || w1 > w || ci_off < 0 || ci_off + c_in > ci_total) return ADN_ERR_ARG;
+    if (!aligned16(dz) || !aligned16(x)) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    CUtensorMap mA, mB[4];
+    st = make_view_map(&mA, dz, n, h, w, c_out, c_out, 0, h, w, 1, 1, 0, 0);
+    if (st != ADN_OK) return st;
+    st = make_view_map(&mB[0], x, n, h1, w1, c_in, c_in, 0, h1, w1, 1, 1, 0, 0);
+    if (st != ADN_OK) return st;
+    mB[1] = mB[2] = mB[3] = mB[0];
+    for (int ky = 0; ky < 3; ++ky) {
+        WgradArgs args{};
+        args.taps = 3;
+        for (int kx = 0; kx < 3; ++kx) {
+            args.tap_dy[kx] = ky - 1; args.tap_dx[kx] = kx - 1; args.tap_map[kx] = 0;
+            args.tap_off[kx] = (long long)ci_off * 9 + ky * 3 + kx;
+        }
+        args.m_total = c_out; args.n_total = c_in;
+        args.sm = (long long)ci_total * 9; args.sn = 9;
+        args.out = d_weight;
+        st = launch_wgrad(mA, mB, args, n, h, w, (cudaStream_t)stream);
+        if (st != ADN_OK) return st;
+    }
+    return ADN_OK;
+}
+
+// d_weight[(ci * c_out + co) * 4 + dy * 2 + dx] += sum_p x[p][ci] * d_up[2p + (dy, dx)][co]   (reference layout (Ci, Co, 2, 2) of
+// model.py:38).  x: (n,h,w,c_in) dense; d_up: channels [up_off, up_off + c_out) of an (n,2h,2w,up_ld) tensor.
+extern "C" int adn_convt2x2_wgrad_f32(const void* x, int c_in, const void* d_up, int up_ld, int up_off, int c_out, int n, int h, int w,
+                                      float* d_weight, void* stream) {
+    if (!x || !d_up || !d_weight || n <= 0 || h <= 0 || w <= 0 || c_out <= 0 || (c_out % 64) || c_in <= 0 || (c_in % 64)) return ADN_ERR_ARG;
+    if (up_off < 0 || up_off + c_out > up_ld || (up_ld % 8) || (up_off % 8)) return ADN_ERR_ARG;
+    if (!aligned16(x) || !aligned16(d_up)) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    CUtensorMap mA, mB[4];
+    st = make_view_map(&mA, x, n, h, w, c_in, c_in, 0, h, w, 1, 1, 0, 0);
+    if (st != ADN_OK) return st;
+    WgradArgs args{};
+    args.taps = 4;
+    for (int q = 0; q < 4; ++q) {
+        st = make_view_map(&mB[q], d_up, n, h, w, c_out, up_ld, up_off, 2 * h, 2 * w, 2, 2, q >> 1, q & 1);
+        if (st != ADN_OK) return st;
+        args.tap_dy[q] = 0; args.tap_dx[q] = 0; args.tap_map[q] = q; args.tap_off[q] = q;
+    }
+    args.m_total = c_in; args.n_total = c_out;
+    args.sm = (long long)c_out * 4; args.sn = 4;
+    args.out = d_weight;
+    return launch_wgrad(mA, mB, args, n, h, w, (cudaStream_t)stream);
+}

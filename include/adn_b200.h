@@ -153,6 +153,86 @@ int64_t adn_loss_workspace_bytes(int64_t batch, int freq, int frames);
 int adn_combined_loss_f32(const float* pred, const float* target, int64_t batch, int freq, int frames,
                           const float* mel_fb_32x64, void* workspace, float* out4, void* stream);
 
+
+/* ------------------------------------------------------------------ training step (code/train.py:65-72)
+ *
+ * train.py:65-72 is zero_grad -> model(noisy) in train() mode -> criterion -> loss.backward() -> clip_grad_norm_(1.0) ->
+ * AdamW.step().  The entry points below are the device side of that body; the host side (audiodenoiser_b200/training.py)
+ * strings them together layer by layer.  Activation gradients are NHWC bf16, parameter gradients fp32 in the reference
+ * state_dict layout.  `workspace` is adn_train_workspace_bytes() bytes of device scratch (256-byte aligned). */
+int64_t adn_train_workspace_bytes(void);
+
+/* Conv3x3 without the activation: out = conv * scale + shift [-> ReLU if relu != 0].  Train-mode pre-BatchNorm output
+ * (scale = 1, shift = conv bias; model.py:11,14 before :12,15) and the data gradient of the backward pass (weights packed by
+ * adn_pack_conv3x3_dgrad_weight_bf16, scale = 1, shift = 0).  Same tcgen05 kernel and argument meaning as
+ * adn_conv3x3_bn_relu_bf16; first-layer (Ci = 1) variant below. */
+int adn_conv3x3_affine_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
+                            const void* w_packed, int c_out, const float* scale, const float* shift, int relu, void* out_bf16,
+                            void* stream);
+int adn_conv3x3_c1_affine_bf16(const float* x, int n, int h, int w, const float* weight, const float* scale, const float* shift,
+                               int relu, void* out_bf16, void* stream);
+
+/* Data-gradient weight packing: conv (Co,Ci,3,3) f32 -> bf16 [Ci][8 - tap][Co]; convT (Ci,Co,2,2) f32 -> bf16 [Ci][q*Co + co]. */
+int adn_pack_conv3x3_dgrad_weight_bf16(const float* w, int c_out, int c_in, void* packed_bf16, void* stream);
+int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int c_out, void* packed_bf16, void* stream);
+
+/* nn.BatchNorm2d in train() mode (model.py:12,15; eps 1e-5, momentum 0.1): batch statistics of z (pixels, c) NHWC bf16 ->
+ * scale = gamma * invstd, shift = beta - mean * scale, mean, invstd; running_mean / running_var are updated in place
+ * (unbiased variance) unless NULL.  Then y = max(z * scale + shift, 0) (BatchNorm + ReLU, model.py:12-13). */
+int adn_bn_train_stats_f32(const void* z_bf16, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
+                           float momentum, float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                           float* invstd, void* workspace, void* stream);
+int adn_bn_relu_apply_bf16(const void* z_bf16, const float* scale, const float* shift, int64_t pixels, int c, void* y_bf16,
+                           void* stream);
+
+/* Backward of ReLU o BatchNorm2d(train): dy (pixel stride dy_ld >= c channels: may be a channel slice) and the saved z ->
+ * dz (dense), d_gamma, d_beta (fp32, overwritten). */
+int adn_bn_relu_backward_bf16(const void* dy_bf16, int dy_ld, const void* z_bf16, int64_t pixels, int c, const float* scale,
+                              const float* shift, const float* mean, const float* invstd, float* d_gamma, float* d_beta,
+                              void* dz_bf16, void* workspace, void* stream);
+
+/* out[ch] = sum over pixels of x[p][ch] (ConvTranspose2d bias gradient; x may be a channel slice with pixel stride x_ld). */
+int adn_channel_sum_f32(const void* x_bf16, int x_ld, int64_t pixels, int c, float* out, void* workspace, void* stream);
+
+/* MaxPool2d(2) backward (gradient to the first maximum of each window, like torch) + the skip-connection gradient
+ * (model.py:31,49): out = d_dec + route(d_pool).  y: the pooled layer's input (n,h,w,c); d_dec may be NULL or a channel slice. */
+int adn_maxpool2x2_backward_add_bf16(const void* y_bf16, const void* d_pool_bf16, const void* d_dec_bf16, int dec_ld, int n, int h,
+                                     int w, int c, void* out_bf16, void* stream);
+
+/* 1x1 head Conv2d(64,1,1) (model.py:68,93): forward (pixels,64) bf16 -> (pixels) fp32; backward -> dy bf16, d_w (64), d_b (1). */
+int adn_head1x1_forward_f32(const void* y_bf16, const float* w, const float* b, int64_t pixels, float* out, void* stream);
+int adn_head1x1_backward(const void* y_bf16, const float* d_out, const float* w, int64_t pixels, void* dy_bf16, float* d_w,
+                         float* d_b, void* workspace, void* stream);
+
+/* Weight gradients, ADDED into fp32 buffers in the reference layout (zero them first: optimizer.zero_grad(), train.py:66).
+ *   conv3x3:  d_weight (Co, ci_total, 3, 3), columns [ci_off, ci_off + c_in) from input x (n,h1,w1,c_in) [(h1,w1) <= (h,w): the
+ *             zero-padded up-sampled half of a concatenated input, model.py:44-49]; tcgen05 GEMM contracting over pixels.
+ *   conv3x3_c1: first layer, d_weight (64,1,3,3), overwritten (deterministic reduction).
+ *   convt2x2: d_weight (Ci, Co, 2, 2); d_up = channels [up_off, up_off + c_out) of an (n,2h,2w,up_ld) gradient tensor. */
+int adn_conv3x3_wgrad_f32(const void* dz_bf16, int c_out, const void* x_bf16, int c_in, int h1, int w1, int n, int h, int w,
+                          float* d_weight, int ci_off, int ci_total, void* stream);
+int adn_conv3x3_c1_wgrad_f32(const void* dz_bf16, const float* x, int n, int h, int w, float* d_weight, void* workspace, void* stream);
+int adn_convt2x2_wgrad_f32(const void* x_bf16, int c_in, const void* d_up_bf16, int up_ld, int up_off, int c_out, int n, int h, int w,
+                           float* d_weight, void* stream);
+
+/* Data gradient of ConvTranspose2d(k=2,s=2): d_in (n,h,w,c_in) from channels [out_off, out_off + c_out) of d_out (n,2h,2w,out_ld). */
+int adn_convt2x2_dgrad_bf16(const void* d_out_bf16, int out_ld, int out_off, int c_out, int n, int h, int w, const void* w_packed,
+                            int c_in, void* d_in_bf16, void* stream);
+
+/* Gradient of c_stft * stft + c_mel * mel + c_l1 * l1 (loss.py:83-95) with respect to pred; train.py:69 is (0.4, 0.4, 0.2). */
+int64_t adn_loss_backward_workspace_bytes(int64_t batch, int freq, int frames);
+int adn_combined_loss_backward_f32(const float* pred, const float* target, int64_t batch, int freq, int frames,
+                                   const float* mel_fb_32x64, float c_stft, float c_mel, float c_l1, void* workspace,
+                                   float* d_pred, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) (train.py:70) over one flat fp32 gradient buffer:
+ * norm_and_coef[0] = total L2 norm, [1] = min(1, max_norm / (norm + 1e-6)).  torch.optim.AdamW.step (train.py:71,124) on flat
+ * buffers, gradients scaled by norm_and_coef[1] (pass NULL for no clipping); `step` is the 1-based step count. */
+int adn_grad_norm_f32(const float* grads, int64_t count, float max_norm, float* norm_and_coef, void* workspace, void* stream);
+int adn_adamw_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                       const float* norm_and_coef, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
