@@ -58,14 +58,16 @@ SIGNATURES = {
     "adn_maxpool2x2_backward_add_bf16": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P]),
     "adn_head1x1_forward_f32": (c_int, [P, P, P, c_int64, P, P]),
     "adn_head1x1_backward": (c_int, [P, P, P, c_int64, P, P, P, P, P]),
-    "adn_conv3x3_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P]),
+    "adn_wgrad_workspace_bytes": (c_int64, []),
+    "adn_conv3x3_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, c_int, P, P]),
     "adn_conv3x3_c1_wgrad_f32": (c_int, [P, P, c_int, c_int, c_int, P, P, P]),
-    "adn_convt2x2_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]),
+    "adn_convt2x2_wgrad_f32": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P]),
     "adn_convt2x2_dgrad_bf16": (c_int, [P, c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P]),
     "adn_loss_backward_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "adn_combined_loss_backward_f32": (c_int, [P, P, c_int64, c_int, c_int, P, c_float, c_float, c_float, P, P, P]),
     "adn_grad_norm_f32": (c_int, [P, c_int64, c_float, P, P, P]),
     "adn_adamw_step_f32": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_int64, P]),
+    "adn_adamw_step_dev_f32": (c_int, [P, P, P, P, c_int64, P, P, c_float, c_float, c_float, c_float, c_float, P]),
 }
 
 

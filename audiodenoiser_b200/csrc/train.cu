@@ -120,10 +120,15 @@ channel_reduce_kernel(const RedArgs a) {
     }
 }
 
-// fixed-order fold of the per-block partials (double accumulation): one thread per (slot, channel)
+// fixed-order fold of the per-block partials (double accumulation) by ONE WARP per (slot, channel): lane l adds blocks l, l + 32,
+// ... in ascending order, then a butterfly combines the 32 lane sums -- the same order every run, and every lane gets the result.
+// Must be called by all 32 lanes of a warp with the same (slot, ch).
 __device__ __forceinline__ double fold_partials(const float* partial, int nb, int ns, int c, int slot, int ch) {
+    const int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = 0; b < nb; ++b) s += (double)partial[((long long)b * ns + slot) * c + ch];
+    for (int b = lane; b < nb; b += 32) s += (double)partial[((long long)b * ns + slot) * c + ch];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;
 }
 
@@ -133,9 +138,10 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
                                        const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
                                        float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
                                        float* __restrict__ mean_out, float* __restrict__ invstd_out) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // one warp per channel
     if (ch >= c) return;
     const double s1 = fold_partials(partial, nb, 2, c, 0, ch), s2 = fold_partials(partial, nb, 2, c, 1, ch);
+    if (threadIdx.x & 31) return;
     const double mean = s1 / count;
     double var = s2 / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -154,13 +160,17 @@ __global__ void bn_finalize_fwd_kernel(const float* __restrict__ partial, int nb
 
 // out[slot][ch] = fold of slot (d_gamma = S2 / d_beta = S1 of the BN backward, bias gradients, head gradients)
 __global__ void fold_kernel(const float* __restrict__ partial, int nb, int ns, int c, int slot, float* __restrict__ out) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch < c) out[ch] = (float)fold_partials(partial, nb, ns, c, slot, ch);
+    const int ch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;       // one warp per channel
+    if (ch >= c) return;
+    const double v = fold_partials(partial, nb, ns, c, slot, ch);
+    if ((threadIdx.x & 31) == 0) out[ch] = (float)v;
 }
 // first-layer weight gradient in the reference layout (64, 1, 3, 3): out[ch * 9 + tap]
 __global__ void fold_c1w_kernel(const float* __restrict__ partial, int nb, float* __restrict__ out) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 576) out[(t & 63) * 9 + (t >> 6)] = (float)fold_partials(partial, nb, 9, 64, t >> 6, t & 63);
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // one warp per (tap, channel)
+    if (t >= 576) return;
+    const double v = fold_partials(partial, nb, 9, 64, t >> 6, t & 63);
+    if ((threadIdx.x & 31) == 0) out[(t & 63) * 9 + (t >> 6)] = (float)v;
 }
 
 // ------------------------------------------------------------------------------------------------ elementwise passes
@@ -332,6 +342,30 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     }
 }
 
+// graph-capturable variant: the 1-based step count lives on the device (step_counter[0], advanced by the launch itself), so a
+// captured training step can be replayed without baking the bias corrections into the graph
+__global__ void adamw_advance_step_kernel(float* __restrict__ step_counter) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) step_counter[0] += 1.f;
+}
+__global__ void __launch_bounds__(TR_THREADS)
+adamw_dev_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                      const float* __restrict__ clip, const float* __restrict__ step_counter, float lr, float beta1, float beta2, float eps,
+                      float weight_decay) {
+    const float t = step_counter[0];
+    const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
+    const float coef = clip ? clip[1] : 1.f;
+    const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        float pi = p[i] * (1.f - lr * weight_decay);
+        const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+        const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+        m[i] = mi; v[i] = vi;
+        pi -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+        p[i] = pi;
+    }
+}
+
 static inline int tr_grid(long long work_items) {
     long long g = (work_items + TR_THREADS - 1) / TR_THREADS;
     long long cap = (long long)num_sms() * 4;
@@ -377,7 +411,7 @@ extern "C" int adn_bn_train_stats_f32(const void* z, int64_t pixels, int c, cons
     int nb = 0;
     int st = launch_reduce<RED_STATS>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
-    bn_finalize_fwd_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, c, (double)pixels, gamma, beta, eps,
+    bn_finalize_fwd_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, c, (double)pixels, gamma, beta, eps,
                                                                               momentum, running_mean, running_var, scale, shift, mean, invstd);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -401,8 +435,8 @@ extern "C" int adn_bn_relu_backward_bf16(const void* dy, int dy_ld, const void* 
     int st = launch_reduce<RED_BNBWD>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
-    fold_kernel<<<(c + 127) / 128, 128, 0, s>>>((const float*)workspace, nb, 2, c, 0, d_beta);
-    fold_kernel<<<(c + 127) / 128, 128, 0, s>>>((const float*)workspace, nb, 2, c, 1, d_gamma);
+    fold_kernel<<<(c * 32 + 255) / 256, 256, 0, s>>>((const float*)workspace, nb, 2, c, 0, d_beta);
+    fold_kernel<<<(c * 32 + 255) / 256, 256, 0, s>>>((const float*)workspace, nb, 2, c, 1, d_gamma);
     bn_relu_bwd_apply_kernel<<<tr_grid(pixels * (c / 8)), TR_THREADS, 0, s>>>((const uint4*)dy, dy_ld / 8, (const uint4*)z, scale, shift, mean, invstd,
                                                                              d_beta, d_gamma, (float)(1.0 / (double)pixels), pixels, c / 8, (uint4*)dz);
     ADN_LAUNCH_CHECK();
@@ -415,7 +449,7 @@ extern "C" int adn_channel_sum_f32(const void* x, int x_ld, int64_t pixels, int 
     int nb = 0;
     int st = launch_reduce<RED_SUM>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
-    fold_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, 1, c, 0, out);
+    fold_kernel<<<(c * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, 1, c, 0, out);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
@@ -447,8 +481,8 @@ extern "C" int adn_head1x1_backward(const void* y, const float* d_out, const flo
     int st = launch_reduce<RED_HEAD>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
-    fold_kernel<<<1, 128, 0, s>>>((const float*)workspace, nb, 2, 64, 0, d_w);
-    fold_kernel<<<1, 32, 0, s>>>((const float*)workspace, nb, 2, 64, 1, d_b);       // only channel 0 of slot 1 is meaningful
+    fold_kernel<<<8, 256, 0, s>>>((const float*)workspace, nb, 2, 64, 0, d_w);
+    fold_kernel<<<8, 256, 0, s>>>((const float*)workspace, nb, 2, 64, 1, d_b);      // d_b: 64 floats, only element 0 is meaningful
     head_bwd_kernel<<<tr_grid(pixels * 8), TR_THREADS, 0, s>>>(d_out, w, pixels, (uint4*)dy);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -461,7 +495,7 @@ extern "C" int adn_conv3x3_c1_wgrad_f32(const void* dz, const float* x, int n, i
     int nb = 0;
     int st = launch_reduce<RED_C1W>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
-    fold_c1w_kernel<<<5, 128, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, d_weight);
+    fold_c1w_kernel<<<72, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, nb, d_weight);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
@@ -484,6 +518,18 @@ extern "C" int adn_adamw_step_f32(float* params, const float* grads, float* exp_
     const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     adamw_kernel<<<tr_grid(count), TR_THREADS, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, norm_and_coef, lr, beta1,
                                                                          beta2, eps, weight_decay, bc1, bc2);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_adamw_step_dev_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                                      const float* norm_and_coef, float* step_counter, float lr, float beta1, float beta2, float eps,
+                                      float weight_decay, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !step_counter || count <= 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    adamw_advance_step_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step_counter);
+    adamw_dev_step_kernel<<<tr_grid(count), TR_THREADS, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, count, norm_and_coef,
+                                                                                  step_counter, lr, beta1, beta2, eps, weight_decay);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

@@ -12,9 +12,11 @@
 //                MN-major SWIZZLE_128B atoms (8 pixel rows x 64 channels = 1024 B): SBO = 1024 B between 8-pixel groups,
 //                LBO = 8192 B between 64-channel blocks.  Tap shifts are TMA coordinates; out-of-image pixels arrive as zeros
 //                (= the conv's zero padding).
-//   split-K      the pixel range is split across CTAs; partial results are added into the fp32 gradient buffer with
-//                red.global.add (the buffer is zeroed by the optimizer's zero_grad, train.py:66).
-//   roles        warp 0: TMA producer - warp 1: tcgen05.mma issuer - warps 2..5: epilogue (tcgen05.ld -> red.add).
+//   split-K      the pixel range is split across CTAs; every CTA stores its fp32 partial tile [split][tap][m][n] to a workspace
+//                with 128-byte row segments, and a second kernel folds the splits in ascending order and adds the result into the
+//                gradient buffer in the reference layout: deterministic, and no scattered atomics (the first version spent 5x
+//                its GEMM time in red.global.add).
+//   roles        warp 0: TMA producer - warp 1: tcgen05.mma issuer - warps 2..5: epilogue (tcgen05.ld -> st.global.v4).
 #include "tc_common.cuh"
 
 namespace adn {
@@ -33,6 +35,8 @@ struct WgradArgs {
     int m_total, n_total;
     long long sm, sn;                          // output strides in elements
     float* out;
+    float* partial;                            // workspace [splits][taps][m_pad][n_pad]
+    int m_pad, n_pad;
     uint32_t lbo, sbo;                         // MN-major descriptor strides (bytes)
 };
 
@@ -137,17 +141,16 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(tfull, 0);
         tc_fence_after();
         for (int t = 0; t < a.taps; ++t) {
+            float4* o = reinterpret_cast<float4*>(a.partial + (((long long)s_idx * a.taps + t) * a.m_pad + m) * a.n_pad + nb * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * BN + c0), r);
                 tmem_ld_wait();
-                if (m < a.m_total) {
-                    float* o = a.out + (long long)m * a.sm + a.tap_off[t] + (long long)(nb * BN + c0) * a.sn;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (nb * BN + c0 + i < a.n_total) atomicAdd(o + (long long)i * a.sn, __uint_as_float(r[i]));
-                }
+                for (int i = 0; i < 8; ++i)
+                    o[(c0 >> 2) + i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                                   __uint_as_float(r[4 * i + 3]));
             }
         }
     }
@@ -157,8 +160,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// debug hook (not part of the public header): MN-major descriptor strides
-static uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024;
+// out[m * sm + n * sn + tap_off[t]] += sum over splits (ascending) of partial[s][t][m][n]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const WgradArgs a) {
+    const long long total = (long long)a.taps * a.m_total * a.n_total;
+    const long long plane = (long long)a.m_pad * a.n_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % a.n_total);
+        const int m = (int)((i / a.n_total) % a.m_total);
+        const int t = (int)(i / ((long long)a.n_total * a.m_total));
+        const float* p = a.partial + (long long)t * plane + (long long)m * a.n_pad + n;
+        float acc = 0.f;
+        for (int s = 0; s < a.splits; ++s) acc += p[(long long)s * a.taps * plane];
+        float* o = a.out + (long long)m * a.sm + (long long)n * a.sn + a.tap_off[t];
+        *o += acc;
+    }
+}
+
+// MN-major SWIZZLE_128B descriptor strides, confirmed by a sweep on B200 (profiles/README.md): LBO = bytes between 64-channel
+// blocks, SBO = bytes between 8-pixel row groups; every other combination produces garbage.
+constexpr uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024;
 
 // a channel slice [c_off, c_off + c) of an NHWC tensor whose pixels are `ld` channels apart, sampled on the (h, w) grid with
 // pixel steps (sy, sx) starting at (oy, ox): element (ch, x, y, img) = base[((img * H_full + oy + sy*y) * W_full + ox + sx*x) * ld + c_off + ch]
@@ -177,7 +198,10 @@ static int make_view_map(CUtensorMap* map, const void* ptr, int n, int h, int w,
     return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
 }
 
-static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs& args, int n, int h, int w, cudaStream_t stream) {
+constexpr long long WG_WORKSPACE_BYTES = 96ll << 20;
+
+static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs& args, int n, int h, int w, void* workspace, cudaStream_t stream) {
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 15)) return ADN_ERR_ARG;
     args.tiles_x = (w + 7) / 8; args.tiles_y = (h + 7) / 8;
     const long long kt = (long long)n * args.tiles_x * args.tiles_y;
     if (kt > 0x7fffffffLL) return ADN_ERR_ARG;
@@ -191,7 +215,13 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
     if (splits < 1) splits = 1;
     // every split must own at least one k-step: shrink until ceil(kt / splits) * (splits - 1) < kt
     while (splits > 1 && (long long)((args.kt_total + splits - 1) / splits) * (splits - 1) >= args.kt_total) --splits;
+    args.m_pad = args.m_blocks * 128; args.n_pad = args.n_blocks * bn;
+    const long long per_split = (long long)args.taps * args.m_pad * args.n_pad * 4;
+    if (per_split > WG_WORKSPACE_BYTES) return ADN_ERR_ARG;
+    if ((long long)splits * per_split > WG_WORKSPACE_BYTES) splits = (int)(WG_WORKSPACE_BYTES / per_split);
+    while (splits > 1 && (long long)((args.kt_total + splits - 1) / splits) * (splits - 1) >= args.kt_total) --splits;
     args.splits = splits;
+    args.partial = static_cast<float*>(workspace);
     args.lbo = g_wg_lbo; args.sbo = g_wg_sbo;
     const int stage_bytes = (2 + args.taps * (bn / 64)) * WG_SUB;
     int stages = (225 * 1024 - 2048) / stage_bytes;
@@ -210,6 +240,10 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
         wgrad_kernel<64><<<grid, WG_THREADS, smem, stream>>>(mA, mB[0], mB[1], mB[2], mB[3], args);
     }
     ADN_LAUNCH_CHECK();
+    const long long total = (long long)args.taps * args.m_total * args.n_total;
+    long long rg = (total + 255) / 256; const long long cap = (long long)num_sms() * 8; if (rg > cap) rg = cap;
+    wgrad_reduce_kernel<<<(int)rg, 256, 0, stream>>>(args);
+    ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
 
@@ -217,13 +251,13 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
 
 using namespace adn;
 
-extern "C" void adn__wgrad_set_desc(int lbo_bytes, int sbo_bytes) { g_wg_lbo = (uint32_t)lbo_bytes; g_wg_sbo = (uint32_t)sbo_bytes; }
+extern "C" int64_t adn_wgrad_workspace_bytes(void) { return WG_WORKSPACE_BYTES; }
 
 // d_weight[(co * ci_total + ci_off + ci) * 9 + ky * 3 + kx] += sum_p dz[p][co] * x[p + (ky-1, kx-1)][ci]   (reference layout
 // (Co, Ci, 3, 3) of model.py:11,14).  dz: (n,h,w,c_out) dense; x: (n,h1,w1,c_in) dense, (h1,w1) <= (h,w) (a zero-padded
 // up-sampled map, model.py:44-47).  ci_off / ci_total address the slice of a concatenated input (model.py:49).
 extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, int c_in, int h1, int w1, int n, int h, int w,
-                                     float* d_weight, int ci_off, int ci_total, void* stream) {
+                                     float* d_weight, int ci_off, int ci_total, void* workspace, void* stream) {
     if (!dz || !x || !d_weight || n <= 0 || h <= 0 || w <= 0 || c_out <= 0 || (c_out % 64) || c_in <= 0 || (c_in % 64)) return ADN_ERR_ARG;
     if (h1 <= 0 || w1 <= 0 || h1 > h || w1 > w || ci_off < 0 || ci_off + c_in > ci_total) return ADN_ERR_ARG;
     if (!aligned16(dz) || !aligned16(x)) return ADN_ERR_ARG;
@@ -244,7 +278,7 @@ extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, i
         args.m_total = c_out; args.n_total = c_in;
         args.sm = (long long)ci_total * 9; args.sn = 9;
         args.out = d_weight;
-        st = launch_wgrad(mA, mB, args, n, h, w, (cudaStream_t)stream);
+        st = launch_wgrad(mA, mB, args, n, h, w, workspace, (cudaStream_t)stream);
         if (st != ADN_OK) return st;
     }
     return ADN_OK;
@@ -253,7 +287,7 @@ extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, i
 // d_weight[(ci * c_out + co) * 4 + dy * 2 + dx] += sum_p x[p][ci] * d_up[2p + (dy, dx)][co]   (reference layout (Ci, Co, 2, 2) of
 // model.py:38).  x: (n,h,w,c_in) dense; d_up: channels [up_off, up_off + c_out) of an (n,2h,2w,up_ld) tensor.
 extern "C" int adn_convt2x2_wgrad_f32(const void* x, int c_in, const void* d_up, int up_ld, int up_off, int c_out, int n, int h, int w,
-                                      float* d_weight, void* stream) {
+                                      float* d_weight, void* workspace, void* stream) {
     if (!x || !d_up || !d_weight || n <= 0 || h <= 0 || w <= 0 || c_out <= 0 || (c_out % 64) || c_in <= 0 || (c_in % 64)) return ADN_ERR_ARG;
     if (up_off < 0 || up_off + c_out > up_ld || (up_ld % 8) || (up_off % 8)) return ADN_ERR_ARG;
     if (!aligned16(x) || !aligned16(d_up)) return ADN_ERR_ARG;
@@ -271,5 +305,5 @@ extern "C" int adn_convt2x2_wgrad_f32(const void* x, int c_in, const void* d_up,
     args.m_total = c_in; args.n_total = c_out;
     args.sm = (long long)c_out * 4; args.sn = 4;
     args.out = d_weight;
-    return launch_wgrad(mA, mB, args, n, h, w, (cudaStream_t)stream);
+    return launch_wgrad(mA, mB, args, n, h, w, workspace, (cudaStream_t)stream);
 }

@@ -77,7 +77,10 @@ class TrainEngine:
         self.ones = torch.ones(1024, dtype=torch.float32, device=dev)
         self.zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.ws = torch.empty(int(self.lib.adn_train_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.wg_ws = torch.empty(int(self.lib.adn_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # AdamW step count, advanced on the device
+        self._graph = None
         self.mel_fb = mel_filterbank().to(dev)
         self.loss_out = torch.empty(4, dtype=torch.float32, device=dev)
         self._loss_ws = None
@@ -251,10 +254,10 @@ class TrainEngine:
                 _lib.check(lib.adn_conv3x3_c1_wgrad_f32(dz.data_ptr(), sv["x"].data_ptr(), n, hh, ww, self._gptr(wkey), wsp, s), "c1 wgrad")
                 self.launch_count += 2
                 return None
-            _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src0.data_ptr(), c0, hh, ww, n, hh, ww, self._gptr(wkey), 0, c0 + c1, s), f"wgrad {wkey}")
+            _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src0.data_ptr(), c0, hh, ww, n, hh, ww, self._gptr(wkey), 0, c0 + c1, self.wg_ws.data_ptr(), s), f"wgrad {wkey}")
             self.launch_count += 3
             if c1:
-                _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src1.data_ptr(), c1, hh, ww, n, hh, ww, self._gptr(wkey), c0, c0 + c1, s), f"wgrad {wkey}")
+                _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src1.data_ptr(), c1, hh, ww, n, hh, ww, self._gptr(wkey), c0, c0 + c1, self.wg_ws.data_ptr(), s), f"wgrad {wkey}")
                 self.launch_count += 3
             if not need_dx:
                 return None
@@ -268,7 +271,7 @@ class TrainEngine:
             layers = list(self.layers)
             head_in = sv["head_in"]
             dy = torch.empty_like(head_in)
-            db = torch.empty(32, dtype=torch.float32, device=self.device)          # element 0 = d out.bias
+            db = torch.empty(64, dtype=torch.float32, device=self.device)          # element 0 = d out.bias
             _lib.check(lib.adn_head1x1_backward(head_in.data_ptr(), d_out.data_ptr(), self._pptr("out.weight"), n * hs[0] * wz[0], dy.data_ptr(),
                                                 self._gptr("out.weight"), db.data_ptr(), wsp, s), "head bwd")
             self.gview("out.bias").copy_(db[:1])
@@ -289,7 +292,7 @@ class TrainEngine:
                 up_ptr = d_cat.data_ptr() + 2 * c
                 _lib.check(lib.adn_channel_sum_f32(up_ptr, 2 * c, n * hs[l] * wz[l], c, self._gptr(f"{name}.bias"), wsp, s), "convT bias grad")
                 _lib.check(lib.adn_convt2x2_wgrad_f32(src.data_ptr(), ci, d_cat.data_ptr(), 2 * c, c, c, n, hs[l + 1], wz[l + 1],
-                                                      self._gptr(f"{name}.weight"), s), "convT wgrad")
+                                                      self._gptr(f"{name}.weight"), self.wg_ws.data_ptr(), s), "convT wgrad")
                 d_src = torch.empty((n, hs[l + 1], wz[l + 1], ci), **bf)
                 _lib.check(lib.adn_convt2x2_dgrad_bf16(d_cat.data_ptr(), 2 * c, c, c, n, hs[l + 1], wz[l + 1], self.packed[name][1].data_ptr(), ci,
                                                        d_src.data_ptr(), s), "convT dgrad")
@@ -344,10 +347,10 @@ class TrainEngine:
         self.step_count += 1
         with torch.cuda.device(self.device):
             _lib.check(lib.adn_grad_norm_f32(self.G.data_ptr(), self.numel, self.max_norm, self.norm_coef.data_ptr(), self.ws.data_ptr(), s), "grad norm")
-            _lib.check(lib.adn_adamw_step_f32(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.numel,
-                                              self.norm_coef.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                                              self.step_count, s), "adamw")
-        self.launch_count += 3
+            _lib.check(lib.adn_adamw_step_dev_f32(self.P.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.V.data_ptr(), self.numel,
+                                                  self.norm_coef.data_ptr(), self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1],
+                                                  self.eps, self.weight_decay, s), "adamw")
+        self.launch_count += 4
         self.repack()
         return self.norm_coef[0]
 
@@ -360,3 +363,31 @@ class TrainEngine:
         self.all_reduce_grads()
         self.optimizer_step()
         return losses
+
+    def train_step_graphed(self, noisy, clean):
+        """train_step through ONE CUDA graph: the step is ~330 small launches, so replaying a captured graph removes the host
+        launch cost.  The first call for a shape runs eagerly (it also performs the one-off cudaFuncSetAttribute calls, which
+        cannot be captured), the second captures and replays, later calls copy the batch into the static inputs and replay."""
+        key = (tuple(noisy.shape), noisy.device)
+        g = self._graph
+        if g is None or g["key"] != key:
+            if g is None or g.get("warm") != key:
+                self._graph = {"key": None, "warm": key}
+                return self.train_step(noisy, clean)
+            static_in = (torch.empty_like(noisy, dtype=torch.float32), torch.empty_like(clean, dtype=torch.float32))
+            static_in[0].copy_(noisy); static_in[1].copy_(clean)
+            graph = torch.cuda.CUDAGraph()
+            count0, launches0 = self.step_count, self.launch_count
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                losses = self.train_step(*static_in)
+            self.step_count = count0                       # capture records the step, it does not execute it
+            self._graph = g = {"key": key, "warm": key, "graph": graph, "in": static_in, "out": losses,
+                               "launches": self.launch_count - launches0}
+            self.launch_count = launches0
+        else:
+            g["in"][0].copy_(noisy, non_blocking=True); g["in"][1].copy_(clean, non_blocking=True)
+        g["graph"].replay()
+        self.step_count += 1
+        self.launch_count += g["launches"]
+        return g["out"]

@@ -364,6 +364,13 @@ def run_b200(args):
                         "sample": f"{len(waves)} clip(s) of the same batch, variant {args.variant}: float64 numpy/scipy STFT -> fp32 torch-CPU "
                                   f"UNet -> {GL_ITERATIONS}-iteration istft/stft loop + istft; {dt:.2f} s"}
 
+    train = None
+    if args.train_steps > 0:
+        del den, job, eager
+        net._ws = {}
+        torch.cuda.empty_cache()
+        train = run_train_bench(args, dev, world, rank, barrier, max_over_ranks)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -383,11 +390,78 @@ def run_b200(args):
             "quality": {"snr_db_vs_clean_mag": stats["snr_db"], "l1_vs_clean_mag": stats["l1"],
                         "combined_perceptual_loss": {k: stats.get(k) for k in ("loss_total", "loss_stft", "loss_mel", "loss_l1")}, "note": "random-init weights: numbers only prove the statistics path runs"},
             "cpu_baseline": cpu_baseline,
+            "train_step": train,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE config 5: the train.py:65-72 step (train-mode forward + CombinedPerceptualLoss + backward + clip + AdamW) on
+    synthetic (B,1,256,64) spectrogram pairs after the loader's float16 round trip, data-parallel over the ranks (one NCCL
+    all-reduce of the flat 31 M-element gradient per step).  Returns the `train_step` object of the JSON line."""
+    import numpy as np
+    import torch
+    from audiodenoiser_b200.checkpoint import seeded_state_dict
+    from audiodenoiser_b200.model import UNet
+    from audiodenoiser_b200.training import TrainEngine
+
+    b = args.train_batch
+    net = UNet()
+    net.load_state_dict(seeded_state_dict(7))
+    eng = TrainEngine(net, lr=1e-4, device=dev)
+    g = torch.Generator().manual_seed(4321 + rank)
+    pairs = []
+    for _ in range(4):                                       # rotating resident batches (activations alone are >> L2)
+        clean = (torch.rand((b, 1, 256, 64), generator=g) * 2.0).half().float()
+        noisy = (clean + 0.3 * torch.rand((b, 1, 256, 64), generator=g)).half().float()
+        pairs.append((noisy.pin_memory(), clean.pin_memory()))
+    dev_pairs = [(a.to(dev), c.to(dev)) for a, c in pairs]
+    steps, warm = args.train_steps, 3
+
+    def timed(fn):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warm + i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    lc0 = eng.launch_count
+    ms_dev = timed(lambda i: eng.train_step_graphed(*dev_pairs[i % 4]))
+    launches = (eng.launch_count - lc0) // (steps + warm)
+
+    def host_step(i):
+        a, c = pairs[i % 4]
+        losses = eng.train_step_graphed(a.to(dev, non_blocking=True), c.to(dev, non_blocking=True))
+        return losses.cpu()                                  # loss.item() of train.py:72 (synchronises)
+    ms_e2e = timed(host_step)
+    losses = eng.train_step_graphed(*dev_pairs[0]).cpu().tolist()
+    flops = 3.0 * unet_flops(256, 64) * b                    # forward + data gradient + weight gradient
+    out = {"workload": f"BASELINE config 5: train.py step, batch {b} x (1,256,64) per GPU, AdamW lr 1e-4, clip 1.0, train-mode BatchNorm",
+           "ms_per_step": ms_dev, "pairs_per_s": b * world / (ms_dev * 1e-3), "e2e_ms_per_step": ms_e2e,
+           "e2e_pairs_per_s": b * world / (ms_e2e * 1e-3), "tflops": flops / (ms_dev * 1e-3) / 1e12, "kernel_launches_per_step": launches, "cuda_graph": True,
+           "h2d_bytes_per_step": 2 * b * 256 * 64 * 4 * world, "d2h_bytes_per_step": 16 * world,
+           "losses_after_warmup": losses, "parallelism": f"ddp{world}: one all_reduce(AVG) of the flat fp32 gradient (31.04 M elements) per step" if world > 1 else "single GPU"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.train_oracle import TrainOracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        nb = min(b, 4)
+        orc = TrainOracle(seeded_state_dict(7), lr=1e-4)
+        a, c = pairs[0]
+        orc.train_step(a[:nb], c[:nb])
+        t0 = time.perf_counter()
+        orc.train_step(a[:nb], c[:nb])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": nb / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "sample": f"one step at batch {nb} of the same pairs: torch-CPU fp32 model.py (train mode) + loss.py + autograd + AdamW; {dt:.2f} s"}
+    return out
 
 
 def unet_workspace_gb(n, h, w):
@@ -434,6 +508,8 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=1, help="clips per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", action="store_true", help="add per-layer timings to the JSON line")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed train.py steps for the `train_step` object (0 = skip)")
+    ap.add_argument("--train-batch", type=int, default=16, help="spectrogram pairs per GPU per training step (train.py default 16)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

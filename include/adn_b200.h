@@ -206,14 +206,16 @@ int adn_head1x1_backward(const void* y_bf16, const float* d_out, const float* w,
 
 /* Weight gradients, ADDED into fp32 buffers in the reference layout (zero them first: optimizer.zero_grad(), train.py:66).
  *   conv3x3:  d_weight (Co, ci_total, 3, 3), columns [ci_off, ci_off + c_in) from input x (n,h1,w1,c_in) [(h1,w1) <= (h,w): the
- *             zero-padded up-sampled half of a concatenated input, model.py:44-49]; tcgen05 GEMM contracting over pixels.
+ *             zero-padded up-sampled half of a concatenated input, model.py:44-49]; tcgen05 GEMM contracting over pixels,
+ *             split-K partials folded in a fixed order (deterministic); wgrad_workspace: adn_wgrad_workspace_bytes() bytes.
  *   conv3x3_c1: first layer, d_weight (64,1,3,3), overwritten (deterministic reduction).
  *   convt2x2: d_weight (Ci, Co, 2, 2); d_up = channels [up_off, up_off + c_out) of an (n,2h,2w,up_ld) gradient tensor. */
+int64_t adn_wgrad_workspace_bytes(void);   /* split-K partial tiles of the two tensor-core weight-gradient entry points */
 int adn_conv3x3_wgrad_f32(const void* dz_bf16, int c_out, const void* x_bf16, int c_in, int h1, int w1, int n, int h, int w,
-                          float* d_weight, int ci_off, int ci_total, void* stream);
+                          float* d_weight, int ci_off, int ci_total, void* wgrad_workspace, void* stream);
 int adn_conv3x3_c1_wgrad_f32(const void* dz_bf16, const float* x, int n, int h, int w, float* d_weight, void* workspace, void* stream);
 int adn_convt2x2_wgrad_f32(const void* x_bf16, int c_in, const void* d_up_bf16, int up_ld, int up_off, int c_out, int n, int h, int w,
-                           float* d_weight, void* stream);
+                           float* d_weight, void* wgrad_workspace, void* stream);
 
 /* Data gradient of ConvTranspose2d(k=2,s=2): d_in (n,h,w,c_in) from channels [out_off, out_off + c_out) of d_out (n,2h,2w,out_ld). */
 int adn_convt2x2_dgrad_bf16(const void* d_out_bf16, int out_ld, int out_off, int c_out, int n, int h, int w, const void* w_packed,
@@ -232,6 +234,11 @@ int adn_grad_norm_f32(const float* grads, int64_t count, float max_norm, float* 
 int adn_adamw_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
                        const float* norm_and_coef, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
                        void* stream);
+/* Same update with the step count kept on the device (step_counter[0], a float the call advances by one before use), so that a
+ * CUDA-graph capture of the whole training step can be replayed. */
+int adn_adamw_step_dev_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t count,
+                           const float* norm_and_coef, float* step_counter, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,6 +49,10 @@ def sp():
     return _lib.stream_ptr()
 
 
+def wgws():
+    return torch.empty(int(_lib.load().adn_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev())
+
+
 @pytest.mark.parametrize("n,h,w,ci,co", [(2, 16, 16, 64, 64), (1, 32, 8, 128, 64), (2, 8, 24, 64, 256)])
 def test_conv3x3_affine_no_relu(n, h, w, ci, co):
     lib = _lib.load()
@@ -145,7 +149,7 @@ def test_head_forward_backward():
     out = torch.empty((n, 1, h, w), dtype=torch.float32, device=d)
     _lib.check(lib.adn_head1x1_forward_f32(yd.data_ptr(), wd.data_ptr(), bd.data_ptr(), pixels, out.data_ptr(), sp()))
     assert torch.allclose(out.cpu(), out_ref.detach(), rtol=1e-5, atol=1e-5)
-    dy = torch.empty_like(yd); dw = torch.empty(64, device=d); dbias = torch.empty(32, device=d)
+    dy = torch.empty_like(yd); dw = torch.empty(64, device=d); dbias = torch.empty(64, device=d)
     wsp = ws()
     dod = d_out.to(d)
     _lib.check(lib.adn_head1x1_backward(yd.data_ptr(), dod.data_ptr(), wd.data_ptr(), pixels, dy.data_ptr(), dw.data_ptr(),
@@ -164,7 +168,8 @@ def test_conv3x3_wgrad_matches_autograd(n, h, w, ci, co):
     F.conv2d(x, wt, padding=1).backward(dz)
     dw = torch.zeros((co, ci, 3, 3), dtype=torch.float32, device=dev())
     dzd, xd = nhwc(dz), nhwc(x)
-    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), co, xd.data_ptr(), ci, h, w, n, h, w, dw.data_ptr(), 0, ci, sp()))
+    wk = wgws()
+    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), co, xd.data_ptr(), ci, h, w, n, h, w, dw.data_ptr(), 0, ci, wk.data_ptr(), sp()))
     assert rel(dw.cpu(), wt.grad) < 2e-3
 
 
@@ -180,8 +185,9 @@ def test_conv3x3_wgrad_concat_slice_and_padded_source():
     F.conv2d(torch.cat([skip, F.pad(up, [0, 1, 0, 1])], dim=1), wt, padding=1).backward(dz)
     dw = torch.zeros((128, 2 * c, 3, 3), dtype=torch.float32, device=dev())
     dzd, skd, upd = nhwc(dz), nhwc(skip), nhwc(up)
-    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), 128, skd.data_ptr(), c, h, w, n, h, w, dw.data_ptr(), 0, 2 * c, sp()))
-    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), 128, upd.data_ptr(), c, h - 1, w - 1, n, h, w, dw.data_ptr(), c, 2 * c, sp()))
+    wk = wgws()
+    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), 128, skd.data_ptr(), c, h, w, n, h, w, dw.data_ptr(), 0, 2 * c, wk.data_ptr(), sp()))
+    _lib.check(lib.adn_conv3x3_wgrad_f32(dzd.data_ptr(), 128, upd.data_ptr(), c, h - 1, w - 1, n, h, w, dw.data_ptr(), c, 2 * c, wk.data_ptr(), sp()))
     assert rel(dw.cpu(), wt.grad) < 2e-3
 
 
@@ -235,7 +241,8 @@ def test_convt2x2_backward(n, h, w, ci, co):
     wide[..., co:] = nhwc(d_up)
     dw = torch.zeros((ci, co, 2, 2), dtype=torch.float32, device=d)
     xd, wtd = nhwc(x), wt.to(d)
-    _lib.check(lib.adn_convt2x2_wgrad_f32(xd.data_ptr(), ci, wide.data_ptr(), 2 * co, co, co, n, h, w, dw.data_ptr(), sp()))
+    wk = wgws()
+    _lib.check(lib.adn_convt2x2_wgrad_f32(xd.data_ptr(), ci, wide.data_ptr(), 2 * co, co, co, n, h, w, dw.data_ptr(), wk.data_ptr(), sp()))
     assert rel(dw.cpu(), wr.grad) < 2e-3
     wp = torch.empty((ci, 4 * co), dtype=torch.bfloat16, device=d)
     _lib.check(lib.adn_pack_convt2x2_dgrad_weight_bf16(wtd.data_ptr(), ci, co, wp.data_ptr(), sp()))

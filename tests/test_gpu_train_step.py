@@ -146,3 +146,17 @@ def test_two_steps_and_state_dict_round_trip():
     eng.model.eval()
     y = eng.model(noisy)
     assert y.shape == noisy.shape and torch.isfinite(y).all()
+
+
+def test_graphed_step_matches_eager():
+    """train_step_graphed (one CUDA-graph replay per step) follows the eager step: same losses step by step (the only
+    run-to-run freedom is the summation order of the split-K weight-gradient atomics)."""
+    noisy, clean = batch(103, (4, 1, 64, 32))
+    noisy, clean = noisy.to(DEV), clean.to(DEV)
+    a, b = _engine(), _engine()
+    for i in range(5):
+        la = a.train_step(noisy, clean).cpu()
+        lb = b.train_step_graphed(noisy, clean).cpu()
+        assert torch.allclose(la, lb, rtol=2e-3), (i, la, lb)
+    assert a.step_count == b.step_count == 5 and float(b.step_dev) == 5.0
+    assert float((a.P - b.P).abs().max()) <= 1.05e-3          # <= 5 steps x 2 lr: the updates are ~lr * sign(g)
