@@ -13,9 +13,9 @@
 //                LBO = 8192 B between 64-channel blocks.  Tap shifts are TMA coordinates; out-of-image pixels arrive as zeros
 //                (= the conv's zero padding).
 //   split-K      the pixel range is split across CTAs; every CTA stores its fp32 partial tile [split][tap][m][n] to a workspace
-//                with 128-byte row segments, and a second kernel folds the splits in ascending order and adds the result into the
-//                gradient buffer in the reference layout: deterministic, and no scattered atomics (the first version spent 5x
-//                its GEMM time in red.global.add).
+//                with 128-byte row segments, and a second kernel folds the splits in ascending order and WRITES the result into
+//                the gradient buffer in the reference layout: deterministic, and no scattered atomics (the first version spent
+//                5x its GEMM time in red.global.add).
 //   roles        warp 0: TMA producer - warp 1: tcgen05.mma issuer - warps 2..5: epilogue (tcgen05.ld -> st.global.v4).
 #include "tc_common.cuh"
 
@@ -24,18 +24,19 @@ namespace adn {
 constexpr int WG_SUB = 64 * 128;               // one [64 px][64 ch] bf16 sub-tile
 constexpr int WG_THREADS = 192;
 constexpr int WG_MAX_STAGES = 6;
-constexpr int WG_MAX_TAPS = 4;
+constexpr int WG_MAX_TAPS = 4;                 // taps per CTA (TMEM: 4 x 128 columns)
+constexpr int WG_MAX_ALL_TAPS = 9;
 
 struct WgradArgs {
     int tiles_x, tiles_y, kt_total;            // 8x8 pixel tiling of the (n, h, w) grid
-    int m_blocks, n_blocks, splits;            // blockIdx.x = (mb * n_blocks + nb) * splits + s
-    int taps, stages;
-    int tap_dy[WG_MAX_TAPS], tap_dx[WG_MAX_TAPS], tap_map[WG_MAX_TAPS];
-    long long tap_off[WG_MAX_TAPS];            // output element offset of each tap
+    int m_blocks, n_blocks, groups, splits;    // blockIdx.x = ((mb * n_blocks + nb) * groups + grp) * splits + s
+    int taps, stages;                          // taps per group (a CTA accumulates one group); groups * taps taps in all
+    int tap_dy[WG_MAX_ALL_TAPS], tap_dx[WG_MAX_ALL_TAPS], tap_map[WG_MAX_ALL_TAPS];
+    long long tap_off[WG_MAX_ALL_TAPS];        // output element offset of each tap
     int m_total, n_total;
     long long sm, sn;                          // output strides in elements
     float* out;
-    float* partial;                            // workspace [splits][taps][m_pad][n_pad]
+    float* partial;                            // workspace [splits][groups * taps][m_pad][n_pad]
     int m_pad, n_pad;
     uint32_t lbo, sbo;                         // MN-major descriptor strides (bytes)
 };
@@ -84,8 +85,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     const int s_idx = blockIdx.x % a.splits;
-    const int mn = blockIdx.x / a.splits;
+    const int rest = blockIdx.x / a.splits;
+    const int grp = rest % a.groups, mn = rest / a.groups;
     const int nb = mn % a.n_blocks, mb = mn / a.n_blocks;
+    const int tap0 = grp * a.taps;                                       // first tap of this CTA's group
     const int per = (a.kt_total + a.splits - 1) / a.splits;
     const int kt0 = s_idx * per, kt1 = min(a.kt_total, kt0 + per);
     const int tiles_per_img = a.tiles_x * a.tiles_y;
@@ -104,10 +107,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tma_load_4d(sa, &tmA, full_bar(stage), mb * 128, x0, y0, img);
                 tma_load_4d(sa + WG_SUB, &tmA, full_bar(stage), mb * 128 + 64, x0, y0, img);
                 for (int t = 0; t < a.taps; ++t) {
-                    const CUtensorMap* mp = (a.tap_map[t] == 0) ? &tmB0 : (a.tap_map[t] == 1) ? &tmB1 : (a.tap_map[t] == 2) ? &tmB2 : &tmB3;
+                    const int gt = tap0 + t;
+                    const CUtensorMap* mp = (a.tap_map[gt] == 0) ? &tmB0 : (a.tap_map[gt] == 1) ? &tmB1 : (a.tap_map[gt] == 2) ? &tmB2 : &tmB3;
                     for (int j = 0; j < NSUB; ++j)
-                        tma_load_4d(sa + (uint32_t)(2 + t * NSUB + j) * WG_SUB, mp, full_bar(stage), nb * BN + j * 64, x0 + a.tap_dx[t],
-                                    y0 + a.tap_dy[t], img);
+                        tma_load_4d(sa + (uint32_t)(2 + t * NSUB + j) * WG_SUB, mp, full_bar(stage), nb * BN + j * 64, x0 + a.tap_dx[gt],
+                                    y0 + a.tap_dy[gt], img);
                 }
                 if (++stage == a.stages) { stage = 0; phase ^= 1u; }
             }
@@ -141,7 +145,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(tfull, 0);
         tc_fence_after();
         for (int t = 0; t < a.taps; ++t) {
-            float4* o = reinterpret_cast<float4*>(a.partial + (((long long)s_idx * a.taps + t) * a.m_pad + m) * a.n_pad + nb * BN);
+            float4* o = reinterpret_cast<float4*>(a.partial + (((long long)s_idx * (a.groups * a.taps) + tap0 + t) * a.m_pad + m) * a.n_pad + nb * BN);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
@@ -160,20 +164,31 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// out[m * sm + n * sn + tap_off[t]] += sum over splits (ascending) of partial[s][t][m][n]
+// out[m * sm + n * sn + tap_off[0] + t] = sum over splits (ascending) of partial[s][t][m][n]  (taps are innermost and contiguous
+// in both reference layouts: sn == number of taps).  One block = one output row m x up to 256 columns n: the partial reads are
+// coalesced along n, the results are transposed through shared memory and leave as ONE contiguous run of 256 x taps floats.
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const WgradArgs a) {
-    const long long total = (long long)a.taps * a.m_total * a.n_total;
+    __shared__ float s_out[256 * WG_MAX_ALL_TAPS];
+    const int all_taps = a.groups * a.taps;
     const long long plane = (long long)a.m_pad * a.n_pad;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(i % a.n_total);
-        const int m = (int)((i / a.n_total) % a.m_total);
-        const int t = (int)(i / ((long long)a.n_total * a.m_total));
-        const float* p = a.partial + (long long)t * plane + (long long)m * a.n_pad + n;
-        float acc = 0.f;
-        for (int s = 0; s < a.splits; ++s) acc += p[(long long)s * a.taps * plane];
-        float* o = a.out + (long long)m * a.sm + (long long)n * a.sn + a.tap_off[t];
-        *o += acc;
+    const int chunks = (a.n_total + 255) / 256;
+    for (int blk = blockIdx.x; blk < a.m_total * chunks; blk += gridDim.x) {
+        const int m = blk / chunks, n0 = (blk - m * chunks) * 256;
+        const int cols = min(256, a.n_total - n0);
+        const int n = n0 + threadIdx.x;
+        if ((int)threadIdx.x < cols) {
+            const float* p = a.partial + (long long)m * a.n_pad + n;
+            for (int t = 0; t < all_taps; ++t) {
+                float acc = 0.f;
+                for (int s = 0; s < a.splits; ++s) acc += p[((long long)s * all_taps + t) * plane];
+                s_out[threadIdx.x * all_taps + t] = acc;
+            }
+        }
+        __syncthreads();
+        float* o = a.out + (long long)m * a.sm + (long long)n0 * a.sn + a.tap_off[0];
+        for (int i = threadIdx.x; i < cols * all_taps; i += 256) o[i] = s_out[i];
+        __syncthreads();
     }
 }
 
@@ -209,16 +224,17 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
     const int bn = (args.n_total % 128 == 0) ? 128 : 64;
     args.m_blocks = (args.m_total + 127) / 128;
     args.n_blocks = (args.n_total + bn - 1) / bn;
-    const int mn = args.m_blocks * args.n_blocks;
-    int splits = (2 * num_sms() + mn - 1) / mn;
-    if (splits > args.kt_total) splits = args.kt_total;
+    const int tiles = args.m_blocks * args.n_blocks * args.groups;
+    // split K so that one wave of CTAs covers the chip, but keep >= 12 k-steps per CTA: every CTA writes a full fp32 partial
+    // tile, so over-splitting a short K turns the GEMM into a workspace-bandwidth problem
+    int splits = (num_sms() + tiles - 1) / tiles;
+    if (splits > args.kt_total / 12) splits = args.kt_total / 12;
     if (splits < 1) splits = 1;
-    // every split must own at least one k-step: shrink until ceil(kt / splits) * (splits - 1) < kt
-    while (splits > 1 && (long long)((args.kt_total + splits - 1) / splits) * (splits - 1) >= args.kt_total) --splits;
     args.m_pad = args.m_blocks * 128; args.n_pad = args.n_blocks * bn;
-    const long long per_split = (long long)args.taps * args.m_pad * args.n_pad * 4;
+    const long long per_split = (long long)args.groups * args.taps * args.m_pad * args.n_pad * 4;
     if (per_split > WG_WORKSPACE_BYTES) return ADN_ERR_ARG;
     if ((long long)splits * per_split > WG_WORKSPACE_BYTES) splits = (int)(WG_WORKSPACE_BYTES / per_split);
+    // every split must own at least one k-step
     while (splits > 1 && (long long)((args.kt_total + splits - 1) / splits) * (splits - 1) >= args.kt_total) --splits;
     args.splits = splits;
     args.partial = static_cast<float*>(workspace);
@@ -229,7 +245,7 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
     if (stages < 2) return ADN_ERR_ARG;
     args.stages = stages;
     const int smem = 1024 + stages * stage_bytes + (2 * WG_MAX_STAGES + 1) * 8 + 16;
-    const int grid = mn * splits;
+    const int grid = tiles * splits;
     if (bn == 128) {
         static unsigned char smem_set[64] = {0};
         ADN_CUDA_TRY(ensure_dyn_smem(wgrad_kernel<128>, 232448, smem_set));
@@ -240,8 +256,8 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
         wgrad_kernel<64><<<grid, WG_THREADS, smem, stream>>>(mA, mB[0], mB[1], mB[2], mB[3], args);
     }
     ADN_LAUNCH_CHECK();
-    const long long total = (long long)args.taps * args.m_total * args.n_total;
-    long long rg = (total + 255) / 256; const long long cap = (long long)num_sms() * 8; if (rg > cap) rg = cap;
+    if (args.sn != args.groups * args.taps) return ADN_ERR_ARG;          // the fold writes contiguous tap runs
+    long long rg = (long long)args.m_total * ((args.n_total + 255) / 256); const long long cap = (long long)num_sms() * 16; if (rg > cap) rg = cap;
     wgrad_reduce_kernel<<<(int)rg, 256, 0, stream>>>(args);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -253,7 +269,7 @@ using namespace adn;
 
 extern "C" int64_t adn_wgrad_workspace_bytes(void) { return WG_WORKSPACE_BYTES; }
 
-// d_weight[(co * ci_total + ci_off + ci) * 9 + ky * 3 + kx] += sum_p dz[p][co] * x[p + (ky-1, kx-1)][ci]   (reference layout
+// d_weight[(co * ci_total + ci_off + ci) * 9 + ky * 3 + kx] = sum_p dz[p][co] * x[p + (ky-1, kx-1)][ci]   (reference layout
 // (Co, Ci, 3, 3) of model.py:11,14).  dz: (n,h,w,c_out) dense; x: (n,h1,w1,c_in) dense, (h1,w1) <= (h,w) (a zero-padded
 // up-sampled map, model.py:44-47).  ci_off / ci_total address the slice of a concatenated input (model.py:49).
 extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, int c_in, int h1, int w1, int n, int h, int w,
@@ -268,23 +284,19 @@ extern "C" int adn_conv3x3_wgrad_f32(const void* dz, int c_out, const void* x, i
     st = make_view_map(&mB[0], x, n, h1, w1, c_in, c_in, 0, h1, w1, 1, 1, 0, 0);
     if (st != ADN_OK) return st;
     mB[1] = mB[2] = mB[3] = mB[0];
-    for (int ky = 0; ky < 3; ++ky) {
-        WgradArgs args{};
-        args.taps = 3;
-        for (int kx = 0; kx < 3; ++kx) {
-            args.tap_dy[kx] = ky - 1; args.tap_dx[kx] = kx - 1; args.tap_map[kx] = 0;
-            args.tap_off[kx] = (long long)ci_off * 9 + ky * 3 + kx;
-        }
-        args.m_total = c_out; args.n_total = c_in;
-        args.sm = (long long)ci_total * 9; args.sn = 9;
-        args.out = d_weight;
-        st = launch_wgrad(mA, mB, args, n, h, w, workspace, (cudaStream_t)stream);
-        if (st != ADN_OK) return st;
+    WgradArgs args{};
+    args.groups = 3; args.taps = 3;                       // a CTA accumulates one kernel row (ky): 3 x BN TMEM columns
+    for (int t = 0; t < 9; ++t) {
+        args.tap_dy[t] = t / 3 - 1; args.tap_dx[t] = t % 3 - 1; args.tap_map[t] = 0;
+        args.tap_off[t] = (long long)ci_off * 9 + t;
     }
-    return ADN_OK;
+    args.m_total = c_out; args.n_total = c_in;
+    args.sm = (long long)ci_total * 9; args.sn = 9;
+    args.out = d_weight;
+    return launch_wgrad(mA, mB, args, n, h, w, workspace, (cudaStream_t)stream);
 }
 
-// d_weight[(ci * c_out + co) * 4 + dy * 2 + dx] += sum_p x[p][ci] * d_up[2p + (dy, dx)][co]   (reference layout (Ci, Co, 2, 2) of
+// d_weight[(ci * c_out + co) * 4 + dy * 2 + dx] = sum_p x[p][ci] * d_up[2p + (dy, dx)][co]   (reference layout (Ci, Co, 2, 2) of
 // model.py:38).  x: (n,h,w,c_in) dense; d_up: channels [up_off, up_off + c_out) of an (n,2h,2w,up_ld) tensor.
 extern "C" int adn_convt2x2_wgrad_f32(const void* x, int c_in, const void* d_up, int up_ld, int up_off, int c_out, int n, int h, int w,
                                       float* d_weight, void* workspace, void* stream) {
@@ -296,7 +308,7 @@ extern "C" int adn_convt2x2_wgrad_f32(const void* x, int c_in, const void* d_up,
     st = make_view_map(&mA, x, n, h, w, c_in, c_in, 0, h, w, 1, 1, 0, 0);
     if (st != ADN_OK) return st;
     WgradArgs args{};
-    args.taps = 4;
+    args.groups = 1; args.taps = 4;
     for (int q = 0; q < 4; ++q) {
         st = make_view_map(&mB[q], d_up, n, h, w, c_out, up_ld, up_off, 2 * h, 2 * w, 2, 2, q >> 1, q & 1);
         if (st != ADN_OK) return st;

@@ -204,7 +204,8 @@ int adn_head1x1_forward_f32(const void* y_bf16, const float* w, const float* b, 
 int adn_head1x1_backward(const void* y_bf16, const float* d_out, const float* w, int64_t pixels, void* dy_bf16, float* d_w,
                          float* d_b, void* workspace, void* stream);
 
-/* Weight gradients, ADDED into fp32 buffers in the reference layout (zero them first: optimizer.zero_grad(), train.py:66).
+/* Weight gradients, WRITTEN to fp32 buffers in the reference layout (every element of the addressed slice is overwritten, which
+ * is what zero_grad() + backward() of train.py:66,69 leaves behind).
  *   conv3x3:  d_weight (Co, ci_total, 3, 3), columns [ci_off, ci_off + c_in) from input x (n,h1,w1,c_in) [(h1,w1) <= (h,w): the
  *             zero-padded up-sampled half of a concatenated input, model.py:44-49]; tcgen05 GEMM contracting over pixels,
  *             split-K partials folded in a fixed order (deterministic); wgrad_workspace: adn_wgrad_workspace_bytes() bytes.
