@@ -144,3 +144,22 @@ class ShardedDenoiser:
                 self._gather_buf = torch.empty(shape, dtype=audio.dtype, device=audio.device)
             audio = all_gather_rows(audio, n_total, self.group, out=self._gather_buf)
         return audio, sums
+
+
+def average_gradients_(flat_grad, group=None):
+    """DDP gradient averaging for the training step (BASELINE config 5): ONE all-reduce over the flat fp32 gradient buffer,
+    in place.  torch DDP semantics: every rank back-propagates the mean loss of its own shard (BatchNorm statistics per
+    replica, the reference has no SyncBN), and the gradients are averaged over the ranks.  NCCL averages in the collective;
+    gloo (the CPU tests) sums and divides."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat_grad
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat_grad
+    if flat_grad.is_cuda:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.div_(world)
+    return flat_grad

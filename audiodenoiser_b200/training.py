@@ -337,9 +337,8 @@ class TrainEngine:
 
     def all_reduce_grads(self):
         """DDP gradient averaging: one NCCL all-reduce over the flat buffer (31.04 M fp32 = 124 MB)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.G, op=dist.ReduceOp.AVG, group=self.group)
+        from .sharding import average_gradients_
+        average_gradients_(self.G, self.group)
 
     def optimizer_step(self):
         """clip_grad_norm_(max_norm) + AdamW.step(), then refresh the bf16 operand copies.  Returns the gradient norm (device scalar)."""
