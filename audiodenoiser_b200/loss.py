@@ -3,7 +3,8 @@
 Same constructor (no arguments), same attributes (``w_stft = 0.4``, ``w_mel = 0.4``, ``w_l1 = 0.2``), same call:
 ``total, stft, mel, l1 = criterion(pred, target)`` with (B, 1, F, T) float32 tensors, returning four 0-dim tensors on the
 inputs' device (test.py:118-122, train.py:68,85).  The arithmetic runs in the CUDA kernels of csrc/loss.cu through
-``adn_combined_loss_f32``.  Forward only in this round (the values carry no autograd graph); no CPU fallback.
+``adn_combined_loss_f32``.  When ``pred`` requires grad the four values are part of the autograd graph: ``loss.backward()``
+(train.py:69) runs ``adn_combined_loss_backward_f32``.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -72,6 +73,44 @@ class _LossKernel:
 _KERNEL = _LossKernel()
 
 
+class _LossFunction(torch.autograd.Function):
+    """(total, stft, mel, l1) = f(pred, target) as one autograd node (gradient with respect to pred only, like train.py needs)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        ctx.save_for_backward(pred, target)
+        return _KERNEL(pred, target)
+
+    @staticmethod
+    def backward(ctx, g4):
+        pred, target = ctx.saved_tensors
+        g = [float(v) for v in g4.detach().cpu().tolist()]
+        c_stft, c_mel, c_l1 = 0.4 * g[0] + g[1], 0.4 * g[0] + g[2], 0.2 * g[0] + g[3]
+        shape = pred.shape
+        p = pred.detach().float().contiguous(); t = target.detach().float().contiguous()
+        if p.dim() == 3:
+            p, t = p.unsqueeze(1), t.unsqueeze(1)
+        b, _, f, tt = p.shape
+        lib = _lib.load()
+        dev = p.device
+        need = int(lib.adn_loss_backward_workspace_bytes(b, f, tt))
+        ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+        d_pred = torch.empty_like(p)
+        if dev not in _KERNEL._fb:
+            _KERNEL._fb[dev] = mel_filterbank().to(dev)
+        with torch.cuda.device(dev):
+            st = lib.adn_combined_loss_backward_f32(p.data_ptr(), t.data_ptr(), b, f, tt, _KERNEL._fb[dev].data_ptr(), c_stft, c_mel, c_l1,
+                                                    ws.data_ptr(), d_pred.data_ptr(), _lib.stream_ptr())
+        _lib.check(st, "adn_combined_loss_backward_f32")
+        return d_pred.reshape(shape), None
+
+
+def _values(pred, target):
+    if torch.is_grad_enabled() and isinstance(pred, torch.Tensor) and pred.requires_grad:
+        return _LossFunction.apply(pred, target)
+    return _KERNEL(pred, target)
+
+
 class MultiScaleSTFTLoss(nn.Module):
     """loss.py:6-35."""
 
@@ -82,7 +121,7 @@ class MultiScaleSTFTLoss(nn.Module):
         self.fft_sizes, self.hop_lengths = list(fft_sizes), list(hop_lengths)
 
     def forward(self, pred, target):
-        return _KERNEL(pred, target)[1]
+        return _values(pred, target)[1]
 
 
 class MelSpectrogramLoss(nn.Module):
@@ -94,7 +133,7 @@ class MelSpectrogramLoss(nn.Module):
             raise ValueError("the B200 build is specialised to the reference's MelSpectrogram(8000, 63, 16, 64)")
 
     def forward(self, pred, target):
-        return _KERNEL(pred, target)[2]
+        return _values(pred, target)[2]
 
 
 class CombinedPerceptualLoss(nn.Module):
@@ -110,7 +149,7 @@ class CombinedPerceptualLoss(nn.Module):
         self.w_l1 = 0.2
 
     def forward(self, pred, target):
-        out = _KERNEL(pred, target)
+        out = _values(pred, target)
         if (self.w_stft, self.w_mel, self.w_l1) != (0.4, 0.4, 0.2):      # weights edited after construction
             total = self.w_stft * out[1] + self.w_mel * out[2] + self.w_l1 * out[3]
         else:

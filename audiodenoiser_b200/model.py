@@ -4,8 +4,10 @@
 libadn_b200.so: bf16 operands, fp32 accumulation in TMEM, fp32 BatchNorm/ReLU epilogues.
 
 The module holds fp32 master parameters in the reference layout; a packed copy (bf16 K-major weights, folded BN
-scale/shift) is rebuilt whenever they change.  Only the eval-mode (running-statistics) forward exists in this round;
-``forward`` in training mode raises.  No CPU path: non-CUDA input raises.
+scale/shift) is rebuilt whenever they change.  In ``train()`` mode ``forward`` runs the batch-statistics kernels of
+``training.TrainEngine`` and returns a tensor that is part of the autograd graph: ``loss.backward()`` runs the hand-written
+backward kernels and deposits ``.grad`` on every parameter, so the reference's train_one_epoch body (train.py:65-72) works
+unchanged with any torch optimizer.  No CPU path: non-CUDA input raises.
 """
 from __future__ import annotations
 
@@ -35,6 +37,24 @@ def _attach(root: nn.Module, dotted: str, tensor: torch.Tensor, is_buffer: bool)
         mod.register_parameter(parts[-1], nn.Parameter(tensor))
 
 
+class _TrainForward(torch.autograd.Function):
+    """model(x) in train() mode as one autograd node: forward = TrainEngine.forward, backward = TrainEngine.backward."""
+
+    @staticmethod
+    def forward(ctx, x, engine, *params):
+        ctx.engine = engine
+        ctx.n_params = len(params)
+        return engine.forward(x)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        eng = ctx.engine
+        eng.zero_grad()
+        eng.backward(d_out)
+        grads = tuple(eng.gview(k).clone() for k in eng.offsets)      # autograd accumulates these into param.grad
+        return (None, None) + grads
+
+
 class UNet(nn.Module):
     """model.py:53-94.  ``UNet(in_channels=1, num_classes=1)``."""
 
@@ -60,6 +80,7 @@ class UNet(nn.Module):
             _attach(self, key, t, is_buffer)
         self._packed = None
         self._packed_key = None
+        self._engine = None
         self._ws = {}
         self.profile = None      # set to a list to record (layer, kind, flops, start_event, end_event) per kernel call
         self.launch_count = 0    # kernels launched by this module so far (bench.py's gpu_launches)
@@ -200,11 +221,29 @@ class UNet(nn.Module):
                       ws["ua0"].data_ptr(), 64, 0, 0, 0, 0, n, h, w, p["w"].data_ptr(), 64, p["scale"].data_ptr(),
                       p["shift"].data_ptr(), pk["out"]["w"].data_ptr(), pk["out"]["b"].data_ptr(), out.data_ptr(), s)
 
+    def train_engine(self, device=None, **optimizer_kwargs):
+        """The TrainEngine bound to this module (created on first use; the module's parameters then alias its flat buffer)."""
+        from .training import TrainEngine
+        if self._engine is None or (device is not None and torch.device(device) != self._engine.device):
+            self._engine = TrainEngine(self, device=device, **optimizer_kwargs)
+        elif optimizer_kwargs:
+            self._engine.set_hyperparameters(**optimizer_kwargs)
+        return self._engine
+
     def forward(self, x):
-        """UNet.forward, model.py:70-94 (eval-mode BatchNorm)."""
+        """UNet.forward, model.py:70-94: eval() -> running-statistics BatchNorm folded into the conv epilogues;
+        train() -> batch-statistics BatchNorm, differentiable (train.py:67,69)."""
         _lib.require_cuda()
+        if not x.is_cuda:
+            raise _lib.AdnError("UNet.forward needs a CUDA tensor (no CPU fallback); move the input with .cuda()")
         if self.training:
-            raise NotImplementedError("audiodenoiser_b200.UNet: only the eval()-mode forward is implemented on the B200 path")
+            if x.dim() != 4 or x.shape[1] != 1:
+                raise ValueError("expected (N, 1, F, T) input")
+            eng = self.train_engine(x.device)
+            eng.refresh_if_parameters_changed()
+            if torch.is_grad_enabled():
+                return _TrainForward.apply(x, eng, *[p for _, p in self.named_parameters()])
+            return eng.forward(x)
         if not x.is_cuda:
             raise _lib.AdnError("UNet.forward needs a CUDA tensor (no CPU fallback); move the input with .cuda()")
         if x.dim() != 4 or x.shape[1] != 1:

@@ -101,9 +101,29 @@ class TrainEngine:
         for (p, ci_, bi, l, c0, c1, co) in self.layers:
             self.stats[(p, ci_)] = tuple(torch.empty(co, dtype=torch.float32, device=dev) for _ in range(4))   # scale, shift, mean, invstd
         self.packed = {}
+        self._packed_versions = None
         self._alloc_packed()
         self.repack()
         self.saved = None
+        self.model._engine = self
+
+    def set_hyperparameters(self, lr=None, betas=None, eps=None, weight_decay=None, max_norm=None):
+        if lr is not None: self.lr = float(lr)
+        if betas is not None: self.betas = tuple(betas)
+        if eps is not None: self.eps = float(eps)
+        if weight_decay is not None: self.weight_decay = float(weight_decay)
+        if max_norm is not None: self.max_norm = float(max_norm)
+        self._graph = None                       # the values are baked into a captured step
+
+    def _versions(self):
+        return tuple(int(p._version) for p in self.model.parameters())
+
+    def refresh_if_parameters_changed(self):
+        """A torch optimizer (or load_state_dict) updates the parameters in place and bumps their version counters; the bf16
+        operand copies are then stale.  (The engine's own optimizer_step repacks by itself.)"""
+        v = self._versions()
+        if v != self._packed_versions:
+            self.repack()
 
     # ------------------------------------------------------------------ views / packing
     def pview(self, key):
@@ -152,6 +172,7 @@ class TrainEngine:
                 _lib.check(lib.adn_pack_convt2x2_dgrad_weight_bf16(wptr, ci, co, wd.data_ptr(), s), "pack convT dgrad")
                 self.launch_count += 2
         self.model._packed = None          # the eval-mode forward of the module repacks from the updated parameters
+        self._packed_versions = self._versions()
 
     # ------------------------------------------------------------------ forward (model.py:70-94 in train() mode)
     def forward(self, x):
