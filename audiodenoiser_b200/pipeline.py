@@ -92,3 +92,60 @@ class Denoiser:
             out_host.copy_(audio, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return out_host
+
+
+def stream_host_batches(step_fn, host_inputs, host_outputs, host_stats=None, device=None):
+    """Run ``step_fn(i, wave_dev) -> (audio_dev, stats_dev | None)`` over a sequence of HOST batches with the host<->device
+    copies overlapped with compute: batch i+1 is copied in and batch i-1 copied out on a second stream while batch i runs.
+
+    host_inputs / host_outputs: lists of pinned host tensors (one per batch; outputs are filled in place); host_stats: optional
+    list of pinned tensors receiving each step's small statistics vector.  Every batch's host->device and device->host copy
+    still happens inside this call -- it is the script-facing entry for a stream of batches, not a way to skip the copies.
+    Two device staging buffers per direction; returns after both streams have drained."""
+    _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    n = len(host_inputs)
+    if n == 0:
+        return host_outputs
+    with torch.cuda.device(dev):
+        comp = torch.cuda.current_stream(dev)
+        copy = torch.cuda.Stream(dev)
+        stage_in = [torch.empty(host_inputs[0].shape, dtype=host_inputs[0].dtype, device=dev) for _ in range(2)]
+        stage_out, stage_stats = [None, None], [None, None]
+        h2d = [torch.cuda.Event() for _ in range(n)]
+        consumed = [None, None]          # compute finished reading stage_in[b]
+        drained = [None, None]           # copy stream finished reading stage_out[b]
+        copy.wait_stream(comp)
+        with torch.cuda.stream(copy):
+            stage_in[0].copy_(host_inputs[0], non_blocking=True)
+            h2d[0].record(copy)
+        for i in range(n):
+            b = i & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy):
+                    if consumed[b ^ 1] is not None:
+                        copy.wait_event(consumed[b ^ 1])
+                    stage_in[b ^ 1].copy_(host_inputs[i + 1], non_blocking=True)
+                    h2d[i + 1].record(copy)
+            comp.wait_event(h2d[i])
+            audio, stats = step_fn(i, stage_in[b])
+            consumed[b] = torch.cuda.Event(); consumed[b].record(comp)
+            if stage_out[b] is None:
+                stage_out[b] = torch.empty(host_outputs[i].shape, dtype=audio.dtype, device=dev)
+                if stats is not None:
+                    stage_stats[b] = torch.empty_like(stats)
+            if drained[b] is not None:
+                comp.wait_event(drained[b])
+            stage_out[b].copy_(audio[: stage_out[b].shape[0]] if audio.shape != stage_out[b].shape else audio)
+            if stats is not None:
+                stage_stats[b].copy_(stats)
+            done = torch.cuda.Event(); done.record(comp)
+            with torch.cuda.stream(copy):
+                copy.wait_event(done)
+                host_outputs[i].copy_(stage_out[b], non_blocking=True)
+                if stats is not None and host_stats is not None:
+                    host_stats[i].copy_(stage_stats[b], non_blocking=True)
+                drained[b] = torch.cuda.Event(); drained[b].record(copy)
+        copy.synchronize()
+        comp.synchronize()
+    return host_outputs

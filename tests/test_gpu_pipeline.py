@@ -58,3 +58,18 @@ def test_denoise_host_buffers(net):
     out = d.denoise_host(x)
     assert out.shape == (2, 23936) and not out.is_cuda
     assert torch.equal(out, d.denoise(x.to(dev())).cpu())
+
+
+def test_stream_host_batches_equals_sequential(net):
+    """The overlapped host-batch stream (copies of neighbouring batches hidden behind compute) returns exactly what
+    batch-at-a-time denoise_host returns, for every batch, with only two staging buffers in flight."""
+    from audiodenoiser_b200.pipeline import stream_host_batches
+    d = Denoiser(net, seed=5)
+    batches = [torch.from_numpy(np.stack([synth.make_clip(10 * b + i, "R") for i in range(2)])).pin_memory() for b in range(5)]
+    ref = [d.denoise_host(x).clone() for x in batches]
+    outs = [torch.empty((2, 23936), dtype=torch.float32).pin_memory() for _ in batches]
+    stats = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in batches]
+    stream_host_batches(lambda i, w: (d.denoise(w), d.denoise(w)[:1, :1].sum().reshape(1)), batches, outs, stats)
+    for o, r, s in zip(outs, ref, stats):
+        assert torch.equal(o, r)
+        assert float(s) == float(r[0, 0])
