@@ -34,11 +34,14 @@ def _world(group):
     return dist.get_world_size(group), dist.get_rank(group)
 
 
-def all_gather_rows(local: torch.Tensor, n_total: int, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+def all_gather_rows(local: torch.Tensor, n_total: int, group=None, out: torch.Tensor | None = None, async_op: bool = False):
     """Gather the row-sharded ``local`` (n_r, ...) of every rank into (n_total, ...) on every rank, in rank order.
 
     Shards follow ``shard_range``: equal blocks of ceil(N/G) rows except the tail.  One ``all_gather_into_tensor`` on a
-    padded (G*per, ...) buffer; the padding rows of the tail ranks are dropped by the final slice (a view)."""
+    padded (G*per, ...) buffer; the padding rows of the tail ranks are dropped by the final slice (a view).
+    ``async_op=True`` returns ``(gathered, work)``: the local shard is first copied into its slot of ``out`` on the current
+    stream (so ``local`` may be overwritten right away) and the collective runs on the backend's stream; ``work.wait()``
+    before reading ``gathered``."""
     world, rank = _world(group)
     if world == 1:
         if local.shape[0] != n_total:
@@ -53,6 +56,13 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None, out: torch.Te
         out = torch.empty((world * per,) + tail, dtype=local.dtype, device=local.device)
     elif tuple(out.shape) != (world * per,) + tail or out.dtype != local.dtype:
         raise ValueError("out must be (world*ceil(N/world), ...) of the local dtype")
+    if async_op:
+        slot = out[rank * per:(rank + 1) * per]
+        slot[: local.shape[0]].copy_(local)
+        if local.shape[0] < per:
+            slot[local.shape[0]:].zero_()
+        work = dist.all_gather_into_tensor(out, slot, group=group, async_op=True)
+        return out[:n_total], work
     if local.shape[0] == per:
         src = local.contiguous()
     else:                                   # tail rank: pad to the common block size
@@ -99,6 +109,9 @@ class ShardedDenoiser:
         self.group = group
         self.world, self.rank = _world(group)
         self._gather_buf = None
+        self._gather_bufs = [None, None]
+        self._gather_work = [None, None]
+        self._gather_turn = 0
         self._sums = None
 
     def local_range(self, n_total: int) -> tuple[int, int]:
@@ -128,16 +141,38 @@ class ShardedDenoiser:
             self._sums[5:8] = torch.stack(terms[1:]).double() * n
         return self._sums
 
-    def step(self, wave_local: torch.Tensor, n_total: int, target_mag_local: torch.Tensor | None = None, gather: bool = True):
+    def finish(self):
+        """Wait for the all-gathers started by ``step(..., overlap_gather=True)``."""
+        for i, w in enumerate(self._gather_work):
+            if w is not None:
+                w.wait()
+                self._gather_work[i] = None
+
+    def step(self, wave_local: torch.Tensor, n_total: int, target_mag_local: torch.Tensor | None = None, gather: bool = True,
+             overlap_gather: bool = False):
         """Denoise this rank's clips; returns (audio, sums): ``audio`` is the gathered (n_total, samples) tensor when
         ``gather`` (every rank gets it, rank order = clip order) else the local shard; ``sums`` is the group-reduced
-        float64 statistics vector (None without a target)."""
+        float64 statistics vector (None without a target).
+
+        ``overlap_gather=True``: the all-gather of this step's audio is started asynchronously into one of two alternating
+        buffers and overlaps the NEXT step's kernels (nothing on the path depends on it); the returned ``audio`` of a step is
+        complete once the step after next has been issued, or after ``finish()``."""
         if target_mag_local is not None:
             audio, _mag, den = self.denoiser.denoise(wave_local, return_spectrograms=True)
             sums = all_reduce_sums(self.error_sums(den, target_mag_local), self.group)
         else:
             audio, sums = self.denoiser.denoise(wave_local), None
-        if gather and self.world > 1:
+        if gather and self.world > 1 and overlap_gather:
+            per = -(-n_total // self.world)
+            shape = (self.world * per,) + tuple(audio.shape[1:])
+            b = self._gather_turn
+            self._gather_turn ^= 1
+            if self._gather_work[b] is not None:            # the gather that last used this buffer
+                self._gather_work[b].wait()
+            if self._gather_bufs[b] is None or tuple(self._gather_bufs[b].shape) != shape or self._gather_bufs[b].device != audio.device:
+                self._gather_bufs[b] = torch.empty(shape, dtype=audio.dtype, device=audio.device)
+            audio, self._gather_work[b] = all_gather_rows(audio, n_total, self.group, out=self._gather_bufs[b], async_op=True)
+        elif gather and self.world > 1:
             per = -(-n_total // self.world)
             shape = (self.world * per,) + tuple(audio.shape[1:])
             if self._gather_buf is None or tuple(self._gather_buf.shape) != shape or self._gather_buf.device != audio.device:

@@ -384,6 +384,11 @@ class TrainEngine:
         self.optimizer_step()
         return losses
 
+    def release_graph(self):
+        """Drop the captured step.  A CUDA graph that contains NCCL kernels must be destroyed BEFORE its process group is
+        (destroy_process_group with such a graph alive deadlocks); call this before tearing the group down."""
+        self._graph = None
+
     def train_step_graphed(self, noisy, clean):
         """train_step through ONE CUDA graph: the step is ~330 small launches, so replaying a captured graph removes the host
         launch cost.  The first call for a shape runs eagerly (it also performs the one-off cudaFuncSetAttribute calls, which

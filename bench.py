@@ -208,7 +208,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
     n_gpus = world
@@ -258,7 +259,7 @@ def run_b200(args):
         return float(t.item())
 
     def step_device(i):
-        audio, sums = job.step(dev_batches[i % rot], n_total, clean_mags[i % rot], gather=True)
+        audio, sums = job.step(dev_batches[i % rot], n_total, clean_mags[i % rot], gather=True, overlap_gather=True)
         return audio, sums
 
     host_outs = [torch.empty((batch, n_out), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -283,6 +284,7 @@ def run_b200(args):
             e0.record()
             for i in range(steps):
                 fn(warmup + i)
+            job.finish()                          # the last steps' overlapped all-gathers complete inside the timed region
             e1.record()
             barrier()
         return max_over_ranks(e0.elapsed_time(e1))
@@ -302,6 +304,7 @@ def run_b200(args):
     t_wall = (time.perf_counter() - t_wall) * 1e3
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), t_wall))      # the call returns after both streams have drained
     audio, sums = step_device(0)
+    job.finish()
     stats = sharding.stats_from_sums(sums.cpu())
     barrier()
 
@@ -392,7 +395,7 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {**workload_config(args, t_frames, batch),
                        "l2": f"inputs rotate over {rot} resident batches; every step rewrites ~{unet_workspace_gb(batch, 257, t_frames):.1f} GB of activations (>> 126 MB L2)",
-                       "collectives": "all_gather(audio) + all_reduce(error sums) per step" if n_gpus > 1 else "none (single GPU)"},
+                       "collectives": "all_gather(audio, overlapped with the next step's kernels) + all_reduce(error sums) per step" if n_gpus > 1 else "none (single GPU)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(batch * length * 4) * n_gpus, "d2h_bytes_per_step": int(batch * n_out * 4 + 32) * n_gpus},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -408,6 +411,8 @@ def run_b200(args):
         }
         emit(line)
     if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -475,6 +480,13 @@ def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": nb / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
                                "sample": f"one step at batch {nb} of the same pairs: torch-CPU fp32 model.py (train mode) + loss.py + autograd + AdamW; {dt:.2f} s"}
+    # the captured step holds NCCL kernels: it has to be gone before destroy_process_group (module <-> engine is a reference cycle)
+    torch.cuda.synchronize()
+    eng.release_graph()
+    net._engine = None
+    del eng, net
+    import gc
+    gc.collect()
     return out
 
 

@@ -44,6 +44,14 @@ def _worker(rank, world, port, n_total, q):
         lo, hi = sharding.shard_range(n_total, world, rank)
         got = sharding.all_gather_rows(full[lo:hi].clone(), n_total)
         ok_gather = torch.equal(got, full)
+        # asynchronous variant: the shard is copied into its slot first, so the source may be overwritten immediately
+        per = -(-n_total // world)
+        buf = torch.full((world * per, 3), -1.0)
+        mine = full[lo:hi].clone()
+        got2, work = sharding.all_gather_rows(mine, n_total, out=buf, async_op=True)
+        mine.fill_(123.0)
+        work.wait()
+        ok_gather = ok_gather and torch.equal(got2, full)
         # statistics: per-rank partial sums -> exact global means
         pred = full[lo:hi] * 0.5
         d = full[lo:hi] - pred
