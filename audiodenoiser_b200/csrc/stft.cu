@@ -18,6 +18,7 @@
 //      no further exchange.
 // Window / twiddle tables are indexed by warp-uniform values only (broadcast shared-memory loads): no registers are
 // spent on them, so pass 2 can hold two rows (64 registers) per thread.
+#define ADN_PACKED_FP32 1            // packed fp32x2 butterflies (see adn_common.cuh)
 #include "adn_common.cuh"
 #include "adn_tables.inc"
 
@@ -101,9 +102,10 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int w = __shfl_sync(0xffffffffu, tid >> 5, 0);          // warp index, provably warp-uniform for the compiler
-    s_hann[tid] = adn_c_hann512_half[tid];
-    s_tw256[tid] = adn_c_tw256[tid >> 4][tid & 15];
-    s_tw512[tid] = adn_c_tw512[tid];
+    // layouts chosen so that the 16 values a warp needs are contiguous: two twiddles / window pairs per 128-bit broadcast load
+    s_hann[tid] = adn_c_hann512_half[16 * (tid & 15) + (tid >> 4)];      // [n2][n1]: window at samples 2(16 n1 + n2), +1
+    s_tw256[tid] = adn_c_tw256[tid >> 4][tid & 15];                      // [n2][k1]
+    s_tw512[tid] = adn_c_tw512[(tid >> 4) + 16 * (tid & 15)];            // [a][k2]: W512^(a + 16 k2)
     const int total_tiles = (int)n_clips * tiles_per_clip;        // < 2^31 (host check)
     const int pad = center ? ADN_N_FFT / 2 : 0;
 
@@ -135,14 +137,21 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
         for (int c = 0; c < 2; ++c) {
             const int n2 = w + 8 * c;
             float2 v[16], tw[16];
+            const float4* hw = reinterpret_cast<const float4*>(s_hann + n2 * 16);
+            const float4* tq = reinterpret_cast<const float4*>(s_tw256 + n2 * 16);
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-                const float2 s = *reinterpret_cast<const float2*>(fr + (n1 >> 2) * ST_ROW_STRIDE + 32 * (n1 & 3) + 2 * n2);
-                const float2 wn = s_hann[16 * n1 + n2];
-                v[n1] = make_float2(s.x * wn.x, s.y * wn.y);
+            for (int j = 0; j < 8; ++j) {
+                const float4 q = hw[j];
+                const float2 s0 = *reinterpret_cast<const float2*>(fr + ((2 * j) >> 2) * ST_ROW_STRIDE + 32 * ((2 * j) & 3) + 2 * n2);
+                const float2 s1 = *reinterpret_cast<const float2*>(fr + ((2 * j + 1) >> 2) * ST_ROW_STRIDE + 32 * ((2 * j + 1) & 3) + 2 * n2);
+                v[2 * j] = pk_mul(s0, make_float2(q.x, q.y));
+                v[2 * j + 1] = pk_mul(s1, make_float2(q.z, q.w));
             }
 #pragma unroll
-            for (int k1 = 1; k1 < 16; ++k1) tw[k1] = s_tw256[n2 * 16 + k1];   // in flight during the butterflies
+            for (int j = 0; j < 8; ++j) {                                // in flight during the butterflies
+                const float4 q = tq[j];
+                tw[2 * j] = make_float2(q.x, q.y); tw[2 * j + 1] = make_float2(q.z, q.w);
+            }
             dft16<false>(v);                                     // over n1: Y[k1]
 #pragma unroll
             for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], tw[k1]);
@@ -167,26 +176,40 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
         dft16<false>(A);                                         // A[k2] = Z[a + 16 k2]
         dft16<false>(B);                                         // B[k2] = Z[b + 16 k2]
         // split in place: zk <- X[k], zp <- conj(X[256-k])
-        auto split = [&](int k, float2& zk, float2& zp) {
-            const float2 e = make_float2(zk.x + zp.x, zk.y - zp.y);
-            const float2 o = make_float2(zk.y + zp.y, zp.x - zk.x);
-            const float2 wo = cmul(o, s_tw512[k]);
+        auto split = [&](float2 tw, float2& zk, float2& zp) {                        // tw = W512^k
+            const float2 e = pk_add(zk, make_float2(zp.x, -zp.y));                    // Zk + conj(Zp)
+            const float2 o = pk_add(rot_mi(zk), make_float2(zp.y, zp.x));             // -i (Zk - conj(Zp))
+            const float2 wo = cmul(o, tw);
             zk = cadd(e, wo);
             zp = csub(e, wo);
         };
+        const float4* twa = reinterpret_cast<const float4*>(s_tw512 + a * 16);        // W512^(a + 16 k2), two per load
+        const float4* twb = reinterpret_cast<const float4*>(s_tw512 + 8 * 16);        // W512^(8 + 16 k2) (warp 0)
         if (w != 0) {
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) split(a + 16 * k2, A[k2], B[15 - k2]);   // 256 - k = b + 16 (15 - k2)
+            for (int j = 0; j < 8; ++j) {                                             // 256 - k = b + 16 (15 - k2)
+                const float4 q = twa[j];
+                split(make_float2(q.x, q.y), A[2 * j], B[15 - 2 * j]);
+                split(make_float2(q.z, q.w), A[2 * j + 1], B[14 - 2 * j]);
+            }
         } else {
             {                                                    // bins 0 and 256 (real): X[0] = 2(Re + Im), X[256] = 2(Re - Im)
                 const float2 z = A[0];
                 A[0] = make_float2(2.f * (z.x + z.y), 2.f * (z.x - z.y));
             }
 #pragma unroll
-            for (int k2 = 1; k2 < 8; ++k2) split(16 * k2, A[k2], A[16 - k2]);
+            for (int j = 0; j < 4; ++j) {
+                const float4 q = twa[j];                                              // a = 0: W512^(16 k2)
+                if (j > 0) split(make_float2(q.x, q.y), A[2 * j], A[16 - 2 * j]);
+                split(make_float2(q.z, q.w), A[2 * j + 1], A[15 - 2 * j]);
+            }
             A[8] = make_float2(2.f * A[8].x, -2.f * A[8].y);     // k = 128 pairs with itself: X[128] = 2 conj(Z[128])
 #pragma unroll
-            for (int k2 = 0; k2 < 8; ++k2) split(8 + 16 * k2, B[k2], B[15 - k2]);
+            for (int j = 0; j < 4; ++j) {
+                const float4 q = twb[j];
+                split(make_float2(q.x, q.y), B[2 * j], B[15 - 2 * j]);
+                split(make_float2(q.z, q.w), B[2 * j + 1], B[14 - 2 * j]);
+            }
         }
         // Where the values live now (row = bin):
         //   w != 0: A[k2] = X[a + 16 k2], B[j] = conj X[b + 16 j]
