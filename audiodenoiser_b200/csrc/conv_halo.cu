@@ -51,13 +51,20 @@ struct HaloArgs {
     float* head_out;
 };
 
-template <int BLOCK_N, bool B_RESIDENT>
+template <int BLOCK_N, bool B_RESIDENT, int NCTA>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmPool, const HaloArgs a) {
-    constexpr int B_BLOCK = BLOCK_N * 128;                         // bytes of one (tap, chunk) weight block
+    // NCTA == 2: a CTA pair (cluster of 2, cta_group::2) computes TWO pixel tiles with ONE 256-row UMMA per k-step.  Each CTA
+    // loads its own halo tile and HALF of the weight block, so the shared-memory operand traffic per CTA and MMA drops from
+    // A + B to A + B/2 bytes -- the single-CTA kernel was measured at the smem->tensor-core operand bandwidth (~64 B/clk).
+    constexpr bool PAIR = (NCTA == 2);
+    constexpr int B_ROWS = BLOCK_N / NCTA;                         // weight rows held by this CTA
+    constexpr int B_BLOCK = B_ROWS * 128;                          // bytes of one (tap, chunk) weight block in this CTA
     constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = (cta_rank == 0);
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -93,122 +100,150 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < H_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
         for (int s = 0; s < H_MAX_B; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), H_EPI_THREADS / 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), NCTA * H_EPI_THREADS / 32); }
         mbar_init(bres, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) { tmem_alloc_pair(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();           // peers must see initialised barriers before any remote arrive
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    // a pair works out of ONE TMEM address in both CTAs: the leader's UMMA writes D at the leader's allocation in each CTA, so
+    // the peer takes the leader's base (its own cta_group::2 allocation is only freed at the end)
+    const uint32_t tmem_own = *tmem_ptr_smem;
+    const uint32_t tmem_base = PAIR ? ld_shared_cluster_u32(mapa_shared(smem_u32(tmem_ptr_smem), 0)) : tmem_own;
 
     const int chunks = a.c0_chunks + a.c1_chunks;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
+    // work items: single CTA -> (m tile, n block); pair -> (pair of m tiles, n block), this CTA taking m = 2*pair + rank
+    const int num_m = a.n_img * tiles_per_img;
+    const int work_total = PAIR ? ((num_m + 1) / 2) * a.n_blocks : a.num_tiles;
+    const int work_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_m = [&](int w) { return PAIR ? 2 * (w / a.n_blocks) + (int)cta_rank : w / a.n_blocks; };
+    // full barriers live in the leader CTA; a peer's TMA completes its bytes there
+    auto full_a_sig = [&](int s) { return PAIR ? mapa_shared(full_a(s), 0) : full_a(s); };
+    auto full_b_sig = [&](int s) { return PAIR ? mapa_shared(full_b(s), 0) : full_b(s); };
 
     if (warp == 0) {
         // ===================================================================== A producer: one halo tile per (tile, chunk)
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                const int m = tile / a.n_blocks;
-                const int img = m / tiles_per_img;
+            for (int w = work_first; w < work_total; w += work_step) {
+                const int m = tile_m(w);
+                const int img = m / tiles_per_img;                // m >= num_m (odd tail of a pair): img == n_img -> all zeros
                 const int rem = m - img * tiles_per_img;
                 const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
                 const int x0 = tx * H_TW - 1, y0 = ty * H_TH - 1;
                 for (int ch = 0; ch < chunks; ++ch) {
                     mbar_wait(empty_a(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_a(stage), H_A_STAGE);
+                    if (leader) mbar_arrive_expect_tx(full_a(stage), NCTA * H_A_STAGE);
                     const uint32_t dst = a_base + (uint32_t)stage * H_A_STAGE;
-                    if (ch < a.c0_chunks) tma_load_4d(dst, &tmA0, full_a(stage), ch * 64, x0, y0, img);
-                    else tma_load_4d(dst, &tmA1, full_a(stage), (ch - a.c0_chunks) * 64, x0, y0, img);
+                    const CUtensorMap* map = (ch < a.c0_chunks) ? &tmA0 : &tmA1;
+                    const int c = (ch < a.c0_chunks ? ch : ch - a.c0_chunks) * 64;
+                    if (PAIR) tma_load_4d_pair(dst, map, full_a_sig(stage), c, x0, y0, img);
+                    else tma_load_4d(dst, map, full_a(stage), c, x0, y0, img);
                     if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 2) {
-        // ===================================================================== B producer
+        // ===================================================================== B producer (this CTA's B_ROWS of every block)
         if (lane == 0) {
+            const int row0 = (int)cta_rank * B_ROWS;
             if (B_RESIDENT) {
-                mbar_arrive_expect_tx(bres, (uint32_t)(9 * chunks) * B_BLOCK);
+                if (leader) mbar_arrive_expect_tx(bres, (uint32_t)(NCTA * 9 * chunks) * B_BLOCK);
+                const uint32_t sig = PAIR ? mapa_shared(bres, 0) : bres;
                 for (int ch = 0; ch < chunks; ++ch)
-                    for (int tap = 0; tap < 9; ++tap)
-                        tma_load_2d(b_base + (uint32_t)(ch * 9 + tap) * B_BLOCK, &tmB, bres, (tap * chunks + ch) * 64, 0);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t dst = b_base + (uint32_t)(ch * 9 + tap) * B_BLOCK;
+                        if (PAIR) tma_load_2d_pair(dst, &tmB, sig, (tap * chunks + ch) * 64, row0);
+                        else tma_load_2d(dst, &tmB, sig, (tap * chunks + ch) * 64, row0);
+                    }
             } else {
                 int slot = 0; uint32_t phase = 0;
-                for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                    const int n_blk = tile % a.n_blocks;
+                for (int w = work_first; w < work_total; w += work_step) {
+                    const int n_blk = w % a.n_blocks;
                     for (int ch = 0; ch < chunks; ++ch)
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(empty_b(slot), phase ^ 1u);
-                            mbar_arrive_expect_tx(full_b(slot), B_BLOCK);
-                            tma_load_2d(b_base + (uint32_t)slot * B_BLOCK, &tmB, full_b(slot), (tap * chunks + ch) * 64, n_blk * BLOCK_N);
+                            if (leader) mbar_arrive_expect_tx(full_b(slot), NCTA * B_BLOCK);
+                            const uint32_t dst = b_base + (uint32_t)slot * B_BLOCK;
+                            if (PAIR) tma_load_2d_pair(dst, &tmB, full_b_sig(slot), (tap * chunks + ch) * 64, n_blk * BLOCK_N + row0);
+                            else tma_load_2d(dst, &tmB, full_b(slot), (tap * chunks + ch) * 64, n_blk * BLOCK_N + row0);
                             if (++slot == a.b_slots) { slot = 0; phase ^= 1u; }
                         }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer (whole warp, one elected lane issues)
+        // ===================================================================== MMA issuer (whole warp, one elected lane issues;
+        // in a CTA pair only the leader's warp issues, for both CTAs)
         // Descriptor arithmetic is hoisted: per stage one base descriptor, per tap / k-step a compile-time constant is added
         // to the 14-bit start-address field (never carries: shared memory is < 256 KB).
-        constexpr uint32_t idesc = make_idesc(BLOCK_N);
-        constexpr uint64_t B_STEP = (uint64_t)(B_BLOCK >> 4);
-        int sa = 0; uint32_t pa = 0;
-        int sb = 0; uint32_t pb = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        if (B_RESIDENT) { mbar_wait(bres, 0); tc_fence_after(); }
-        const uint64_t db_base = make_sw128_desc(b_base);
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            mbar_wait(tempty(acc), acc_phase ^ 1u);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int ch = 0; ch < chunks; ++ch) {
-                mbar_wait(full_a(sa), pa);
+        if (leader) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N, 128 * NCTA);
+            constexpr uint64_t B_STEP = (uint64_t)(B_BLOCK >> 4);
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accf) {
+                if (PAIR) umma_bf16_pair(d, da, db, idesc, accf); else umma_bf16(d, da, db, idesc, accf);
+            };
+            auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            if (B_RESIDENT) { mbar_wait(bres, 0); tc_fence_after(); }
+            const uint64_t db_base = make_sw128_desc(b_base);
+            for (int w = work_first; w < work_total; w += work_step) {
+                mbar_wait(tempty(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                // measured on B200: the UMMA swizzle is a function of the absolute shared-memory address bits (like TMA's), so
-                // a tap view that starts dx rows into a 1024-byte atom needs NO descriptor base offset
-                const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * H_A_STAGE, H_PITCH * 128);
-                if (B_RESIDENT) {
-                    const uint64_t db_chunk = db_base + (uint64_t)(ch * 9) * B_STEP;
-                    if (elect_one()) {
-#pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
-                            const uint64_t db = db_chunk + (uint64_t)tap * B_STEP;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)                  // UMMA_K = 16: +32 bytes inside the swizzle row
-                                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
-                        }
-                        umma_commit(empty_a(sa));
-                    }
-                    __syncwarp();
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(full_b(sb), pb);
-                        tc_fence_after();
-                        const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
-                        const uint64_t db = db_base + (uint64_t)sb * B_STEP;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(full_a(sa), pa);
+                    tc_fence_after();
+                    // measured on B200: the UMMA swizzle is a function of the absolute shared-memory address bits (like TMA's),
+                    // so a tap view that starts dx rows into a 1024-byte atom needs NO descriptor base offset
+                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * H_A_STAGE, H_PITCH * 128);
+                    if (B_RESIDENT) {
+                        const uint64_t db_chunk = db_base + (uint64_t)(ch * 9) * B_STEP;
                         if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
-                            umma_commit(empty_b(sb));
-                            if (tap == 8) umma_commit(empty_a(sa));
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
+                                const uint64_t db = db_chunk + (uint64_t)tap * B_STEP;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)              // UMMA_K = 16: +32 bytes inside the swizzle row
+                                    mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                            }
+                            commit(empty_a(sa));
                         }
                         __syncwarp();
-                        if (++sb == a.b_slots) { sb = 0; pb ^= 1u; }
+                    } else {
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(full_b(sb), pb);
+                            tc_fence_after();
+                            const uint64_t da = da_stage + (uint64_t)(((tap / 3) * H_PITCH + (tap % 3)) * 8);
+                            const uint64_t db = db_base + (uint64_t)sb * B_STEP;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    mma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), (tap | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                                commit(empty_b(sb));
+                                if (tap == 8) commit(empty_a(sa));
+                            }
+                            __syncwarp();
+                            if (++sb == a.b_slots) { sb = 0; pb ^= 1u; }
+                        }
                     }
+                    if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
                 }
-                if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
+                if (elect_one()) commit(tfull(acc));
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (elect_one()) umma_commit(tfull(acc));
-            __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
         // ===================================================================== epilogue (warps 3..6 = TMEM lane quadrants 3,0,1,2)
@@ -222,14 +257,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const int Hp = a.H >> 1, Wp = a.W >> 1;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-            const int n_blk = tile % a.n_blocks;
-            const int m = tile / a.n_blocks;
-            const int img = m / tiles_per_img;
+        const uint32_t tempty_sig0 = PAIR ? mapa_shared(tempty(0), 0) : tempty(0);
+        const uint32_t tempty_sig1 = PAIR ? mapa_shared(tempty(1), 0) : tempty(1);
+        for (int w = work_first; w < work_total; w += work_step) {
+            const int n_blk = w % a.n_blocks;
+            const int m = tile_m(w);
+            const int img = m / tiles_per_img;                      // == n_img for the padding tile of an odd pair
             const int rem = m - img * tiles_per_img;
             const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
             const int x = tx * H_TW + lx, y = ty * H_TH + ly;
-            const bool valid = (x < a.W) && (y < a.H);
+            const bool valid = (x < a.W) && (y < a.H) && (m < num_m);
             // pooled pixel owned by this lane: lanes with even (lx, ly); its 2x2 window = lanes ^1, ^8, ^9 of the same warp
             const bool pool_writer = a.pool_out && !(lx & 1) && !(ly & 1) && (x >> 1) < Wp && (y >> 1) < Hp;
 
@@ -324,23 +361,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 a.head_out[((long long)img * a.H + y) * a.W + x] = head_acc + a.head_b[0];
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(acc));                 // 4 arrivals (one per epilogue warp) free the accumulator
+            if (lane == 0) {                                         // one arrival per epilogue warp (of both CTAs) frees the accumulator
+                if (PAIR) mbar_arrive_cluster(acc ? tempty_sig1 : tempty_sig0); else mbar_arrive(tempty(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (a.tma_store && et == 0) bulk_wait<0>();                    // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();           // the peer may still read this CTA's smem / write its TMEM
     tc_fence_after();
-    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem_own, TMEM_COLS); else tmem_dealloc(tmem_own, TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-template <int BLOCK_N>
+static int g_pair_mode = 1;      // 0: never use CTA pairs; 1: where the layer is shared-memory-operand bound and a pair pays off
+
+template <int BLOCK_N, int NCTA>
 static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const CUtensorMap& mOut,
                        const CUtensorMap& mPool, HaloArgs& args, int chunks, cudaStream_t stream) {
-    constexpr int B_BLOCK = BLOCK_N * 128;
+    constexpr int B_BLOCK = (BLOCK_N / NCTA) * 128;              // bytes of one (tap, chunk) weight block in ONE CTA
     const int AUX = (2 * args.c_out + 64) * 4 + (2 * H_MAX_A + 2 * H_MAX_B + 5) * 8 + 16;
     constexpr int MAX_DYN = 232448;
     const int budget = MAX_DYN - 1024 - AUX;
@@ -366,15 +407,33 @@ static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUt
     }
     const int smem = 1024 + args.a_stages * H_A_STAGE + args.b_slots * B_BLOCK + (args.tma_store ? staging : 0) + AUX;
     const int sms = num_sms();
-    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    int grid;
+    if (NCTA == 2) {
+        const int num_m = args.n_img * args.tiles_x * args.tiles_y;
+        const int pairs = ((num_m + 1) / 2) * args.n_blocks;
+        const int max_pairs = sms / 2;
+        grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
+    } else {
+        grid = args.num_tiles < sms ? args.num_tiles : sms;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(H_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (NCTA == 2) ? 1 : 0;
     if (args.b_resident) {
         static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true>, MAX_DYN, smem_set));
-        conv3x3_halo_kernel<BLOCK_N, true><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true, NCTA>, MAX_DYN, smem_set));
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, true, NCTA>, mA0, mA1, mB, mOut, mPool, args));
     } else {
         static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false>, MAX_DYN, smem_set));
-        conv3x3_halo_kernel<BLOCK_N, false><<<grid, H_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false, NCTA>, MAX_DYN, smem_set));
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, false, NCTA>, mA0, mA1, mB, mOut, mPool, args));
     }
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -414,7 +473,14 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     if (st != ADN_OK) return st;
     if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, H_PITCH, H_ROWS); else mA1 = mA0;
     if (st != ADN_OK) return st;
-    st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), block_n);
+    // CTA pairs (cta_group::2): two pixel tiles per 256-row UMMA, each CTA holding half of the weight rows.  Used where one CTA is
+    // bound by the shared-memory operand reads (BLOCK_N 64 / 128: A + B bytes per MMA exceed 128 B/clk), and only when every
+    // SM pair still gets work
+    const int num_m = n * args.tiles_x * args.tiles_y;
+    // measured (variant B, batch 64): 128-wide layers with >= 2 input chunks gain 8-32 % (upconv3.0: 1 171 -> 1 548 TFLOP/s);
+    // 64-wide layers LOSE 30 % in pair mode (a 256x64 UMMA is too short to amortise), so they stay single-CTA
+    const bool pair = g_pair_mode && block_n == 128 && (c0 + c1) >= 128 && args.n_blocks == 1 && num_m >= 2 * (num_sms() / 2);
+    st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), pair ? block_n / 2 : block_n);
     if (st != ADN_OK) return st;
 
     // output maps for the TMA-store epilogue: box {64 ch, 8 px, 16 rows} of the NHWC output, {64, 4, 8} of the pooled one
@@ -428,13 +494,17 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
 
     const int chunks = args.c0_chunks + args.c1_chunks;
     switch (block_n) {
-        case 256: return launch_halo<256>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
-        case 128: return launch_halo<128>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
-        default: return launch_halo<64>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        case 256: return launch_halo<256, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        case 128: return pair ? launch_halo<128, 2>(mA0, mA1, mB, mOut, mPool, args, chunks, stream)
+                              : launch_halo<128, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        default: return launch_halo<64, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
     }
 }
 
 }  // namespace adn
+
+// tuning / debugging hook (not in the public header): 0 disables the CTA-pair kernels
+extern "C" void adn__conv_pair_mode(int mode) { adn::g_pair_mode = mode; }
 
 extern "C" int adn_conv3x3_bn_relu_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
                                         const void* w_packed, int c_out, const float* scale, const float* shift, void* out,
