@@ -355,6 +355,14 @@ def run_b200(args):
                     "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                     "launches_per_step": tc["launches"] // reps, "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),
                     "algorithmic_flops_per_step": tc["flops"] / reps, "traffic": None}
+        try:                                   # measured DRAM bytes per launch of the same kernel, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get(args.variant)
+            if tr and tr["batch"] == batch:
+                roofline["traffic"] = tr["dram_bytes_per_launch"]
+                roofline["traffic_unit"] = "bytes per launch (dram read + write, ncu --set full)"
+                roofline["algorithmic_bytes_per_launch"] = unet_conv_bytes(batch, 257, t_frames) / max(tc["launches"] // reps, 1)
+        except Exception:  # noqa: BLE001
+            pass
         stft_ms = float(np.mean([a.elapsed_time(b) for a, b in spans["stft"]]))
         istft_ms = float(np.mean([a.elapsed_time(b) for a, b in spans["istft"]]))
         stft_bytes = batch * (4 * length + 4 * 257 * t_frames)
@@ -488,6 +496,28 @@ def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
     import gc
     gc.collect()
     return out
+
+
+def unet_conv_bytes(n, h, w):
+    """Activation bytes (bf16, in + out, + pooled outputs) the 17 tensor-core conv launches of one forward must move."""
+    hs, ws = [h], [w]
+    for _ in range(4):
+        hs.append(hs[-1] // 2); ws.append(ws[-1] // 2)
+    ch = [64, 128, 256, 512, 1024]
+    px = [n * hs[l] * ws[l] for l in range(5)]
+    total = 0
+    for l in range(5):
+        cin = ch[l - 1] if l else None
+        if l:
+            total += px[l] * (cin + ch[l]) * 2                          # first conv of the level (level 0's is the Cin=1 direct conv)
+        total += px[l] * (ch[l] + ch[l]) * 2                            # second conv
+        if l < 4:
+            total += px[l + 1] * ch[l] * 2                              # fused max-pool output
+    for l in (3, 2, 1, 0):
+        total += px[l] * (2 * ch[l] + ch[l]) * 2                        # conv over [skip, up]
+        total += px[l] * (ch[l] + (ch[l] if l else 0)) * 2              # second conv (level 0: fused head, fp32 out below)
+    total += px[0] * 4
+    return float(total)
 
 
 def unet_workspace_gb(n, h, w):
