@@ -165,6 +165,14 @@ __global__ void fold_kernel(const float* __restrict__ partial, int nb, int ns, i
     const double v = fold_partials(partial, nb, ns, c, slot, ch);
     if ((threadIdx.x & 31) == 0) out[ch] = (float)v;
 }
+// both slots of a 2-slot reduction in one launch (BN backward: slot 0 -> d_beta, slot 1 -> d_gamma): one warp per (slot, channel)
+__global__ void fold2_kernel(const float* __restrict__ partial, int nb, int c, float* __restrict__ out0, float* __restrict__ out1) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= 2 * c) return;
+    const int slot = t / c, ch = t - slot * c;
+    const double v = fold_partials(partial, nb, 2, c, slot, ch);
+    if ((threadIdx.x & 31) == 0) (slot ? out1 : out0)[ch] = (float)v;
+}
 // first-layer weight gradient in the reference layout (64, 1, 3, 3): out[ch * 9 + tap]
 __global__ void fold_c1w_kernel(const float* __restrict__ partial, int nb, float* __restrict__ out) {
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;        // one warp per (tap, channel)
@@ -435,8 +443,7 @@ extern "C" int adn_bn_relu_backward_bf16(const void* dy, int dy_ld, const void* 
     int st = launch_reduce<RED_BNBWD>(a, &nb, (cudaStream_t)stream);
     if (st != ADN_OK) return st;
     cudaStream_t s = (cudaStream_t)stream;
-    fold_kernel<<<(c * 32 + 255) / 256, 256, 0, s>>>((const float*)workspace, nb, 2, c, 0, d_beta);
-    fold_kernel<<<(c * 32 + 255) / 256, 256, 0, s>>>((const float*)workspace, nb, 2, c, 1, d_gamma);
+    fold2_kernel<<<(2 * c * 32 + 255) / 256, 256, 0, s>>>((const float*)workspace, nb, c, d_beta, d_gamma);
     bn_relu_bwd_apply_kernel<<<tr_grid(pixels * (c / 8)), TR_THREADS, 0, s>>>((const uint4*)dy, dy_ld / 8, (const uint4*)z, scale, shift, mean, invstd,
                                                                              d_beta, d_gamma, (float)(1.0 / (double)pixels), pixels, c / 8, (uint4*)dz);
     ADN_LAUNCH_CHECK();

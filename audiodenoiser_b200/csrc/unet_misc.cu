@@ -53,6 +53,51 @@ __global__ void pack_convt2x2_dgrad_kernel(const float* __restrict__ w, int ci_n
     }
 }
 
+// One launch for every layer: forward and data-gradient packs of all conv / convT weights after an optimizer step.
+// blockIdx.y = table entry, blockIdx.x strides over that tensor's elements (destination-ordered: coalesced bf16 writes).
+struct PackEntry {
+    const float* w;
+    __nv_bfloat16* fwd;
+    __nv_bfloat16* dgrad;
+    int c_out, c_in, kind, pad;          // kind 0: Conv2d 3x3 (Co,Ci,3,3); 1: ConvTranspose2d 2x2 (Ci,Co,2,2)
+};
+__global__ void __launch_bounds__(256)
+pack_table_kernel(const PackEntry* __restrict__ table) {
+    const PackEntry e = table[blockIdx.y];
+    const int co_n = e.c_out, ci_n = e.c_in;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (e.kind == 0) {
+        const long long total = (long long)co_n * 9 * ci_n;
+        for (long long i = i0; i < total; i += stride) {          // fwd [co][tap][ci]
+            const int ci = (int)(i % ci_n);
+            const int tap = (int)((i / ci_n) % 9);
+            const int co = (int)(i / ((long long)ci_n * 9));
+            e.fwd[i] = __float2bfloat16_rn(e.w[((long long)co * ci_n + ci) * 9 + tap]);
+        }
+        for (long long i = i0; i < total; i += stride) {          // dgrad [ci][8 - tap][co]
+            const int co = (int)(i % co_n);
+            const int tap = (int)((i / co_n) % 9);
+            const int ci = (int)(i / ((long long)co_n * 9));
+            e.dgrad[i] = __float2bfloat16_rn(e.w[((long long)co * ci_n + ci) * 9 + (8 - tap)]);
+        }
+    } else {
+        const long long total = 4ll * co_n * ci_n;
+        for (long long i = i0; i < total; i += stride) {          // fwd [q][co][ci]
+            const int ci = (int)(i % ci_n);
+            const int co = (int)((i / ci_n) % co_n);
+            const int q = (int)(i / ((long long)ci_n * co_n));
+            e.fwd[i] = __float2bfloat16_rn(e.w[((long long)ci * co_n + co) * 4 + q]);
+        }
+        for (long long i = i0; i < total; i += stride) {          // dgrad [ci][q * Co + co]
+            const int co = (int)(i % co_n);
+            const int q = (int)((i / co_n) % 4);
+            const int ci = (int)(i / (4ll * co_n));
+            e.dgrad[i] = __float2bfloat16_rn(e.w[((long long)ci * co_n + co) * 4 + q]);
+        }
+    }
+}
+
 __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var, float eps, int c,
                                float* __restrict__ scale, float* __restrict__ shift) {
@@ -260,6 +305,14 @@ extern "C" int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int
     if (!w || !packed || c_out <= 0 || c_in <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
     pack_convt2x2_dgrad_kernel<<<grid_for(4ll * c_out * c_in), 256, 0, (cudaStream_t)stream>>>(w, c_in, c_out, (__nv_bfloat16*)packed);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stream) {
+    if (!table_dev || n_entries <= 0 || n_entries > 65535) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    pack_table_kernel<<<dim3(1024, (unsigned)n_entries), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev));
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

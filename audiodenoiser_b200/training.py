@@ -101,6 +101,7 @@ class TrainEngine:
         for (p, ci_, bi, l, c0, c1, co) in self.layers:
             self.stats[(p, ci_)] = tuple(torch.empty(co, dtype=torch.float32, device=dev) for _ in range(4))   # scale, shift, mean, invstd
         self.packed = {}
+        self._pack_table = None
         self._packed_versions = None
         self._alloc_packed()
         self.repack()
@@ -151,26 +152,33 @@ class TrainEngine:
             ci, co = _CH[l + 1], _CH[l]
             self.packed[f"upconv{i + 1}.up"] = (torch.empty((4, co, ci), **bf), torch.empty((ci, 4 * co), **bf))
 
+    def _build_pack_table(self):
+        import numpy as np
+        rec = np.dtype([("w", np.uint64), ("fwd", np.uint64), ("dgrad", np.uint64), ("c_out", np.int32), ("c_in", np.int32),
+                        ("kind", np.int32), ("pad", np.int32)])
+        rows = []
+        for (p, ci_, bi, l, c0, c1, co) in self.layers:
+            cin = c0 + c1
+            if cin == 1:
+                continue
+            wf, wd = self.packed[(p, ci_)]
+            rows.append((self._pptr(f"{p}.double_conv.{ci_}.weight"), wf.data_ptr(), wd.data_ptr(), co, cin, 0, 0))
+        for i, l in enumerate((3, 2, 1, 0)):
+            ci, co = _CH[l + 1], _CH[l]
+            wf, wd = self.packed[f"upconv{i + 1}.up"]
+            rows.append((self._pptr(f"upconv{i + 1}.up.weight"), wf.data_ptr(), wd.data_ptr(), co, ci, 1, 0))
+        host = np.array(rows, dtype=rec)
+        self._pack_n = len(rows)
+        self._pack_table = torch.from_numpy(host.view(np.uint8).copy()).to(self.device)
+
     def repack(self):
-        """fp32 master weights -> bf16 GEMM operands (forward [Co][tap][Ci], data gradient [Ci][8-tap][Co]); once per step."""
-        lib, s = self.lib, _lib.stream_ptr()
+        """fp32 master weights -> bf16 GEMM operands (forward [Co][tap][Ci], data gradient [Ci][8-tap][Co]; convT likewise): one
+        launch over a device-side table of all 21 conv / convT weights, once per optimizer step."""
+        if self._pack_table is None:
+            self._build_pack_table()
         with torch.cuda.device(self.device):
-            for (p, ci_, bi, l, c0, c1, co) in self.layers:
-                cin = c0 + c1
-                if cin == 1:
-                    continue
-                wf, wd = self.packed[(p, ci_)]
-                wptr = self._pptr(f"{p}.double_conv.{ci_}.weight")
-                _lib.check(lib.adn_pack_conv3x3_weight_bf16(wptr, co, cin, wf.data_ptr(), s), "pack conv")
-                _lib.check(lib.adn_pack_conv3x3_dgrad_weight_bf16(wptr, co, cin, wd.data_ptr(), s), "pack conv dgrad")
-                self.launch_count += 2
-            for i, l in enumerate((3, 2, 1, 0)):
-                ci, co = _CH[l + 1], _CH[l]
-                wf, wd = self.packed[f"upconv{i + 1}.up"]
-                wptr = self._pptr(f"upconv{i + 1}.up.weight")
-                _lib.check(lib.adn_pack_convt2x2_weight_bf16(wptr, ci, co, wf.data_ptr(), s), "pack convT")
-                _lib.check(lib.adn_pack_convt2x2_dgrad_weight_bf16(wptr, ci, co, wd.data_ptr(), s), "pack convT dgrad")
-                self.launch_count += 2
+            _lib.check(self.lib.adn_pack_weights_table_bf16(self._pack_table.data_ptr(), self._pack_n, _lib.stream_ptr()), "pack weights")
+        self.launch_count += 1
         self.model._packed = None          # the eval-mode forward of the module repacks from the updated parameters
         self._packed_versions = self._versions()
 

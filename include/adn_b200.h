@@ -176,6 +176,11 @@ int adn_conv3x3_c1_affine_bf16(const float* x, int n, int h, int w, const float*
 int adn_pack_conv3x3_dgrad_weight_bf16(const float* w, int c_out, int c_in, void* packed_bf16, void* stream);
 int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int c_out, void* packed_bf16, void* stream);
 
+/* All weight packs of a training step in ONE launch.  table_dev: device array of n_entries records
+ *   struct { const float* w; void* fwd_bf16; void* dgrad_bf16; int32_t c_out, c_in, kind, pad; }   (32 bytes)
+ * kind 0 = Conv2d 3x3 (fwd [Co][tap][Ci], dgrad [Ci][8-tap][Co]); kind 1 = ConvTranspose2d 2x2 (fwd [q][Co][Ci], dgrad [Ci][q*Co+co]). */
+int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stream);
+
 /* nn.BatchNorm2d in train() mode (model.py:12,15; eps 1e-5, momentum 0.1): batch statistics of z (pixels, c) NHWC bf16 ->
  * scale = gamma * invstd, shift = beta - mean * scale, mean, invstd; running_mean / running_var are updated in place
  * (unbiased variance) unless NULL.  Then y = max(z * scale + shift, 0) (BatchNorm + ReLU, model.py:12-13). */
