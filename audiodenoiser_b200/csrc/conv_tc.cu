@@ -7,7 +7,7 @@
 //                 TMEM lanes), landing as a K-major SWIZZLE_128B tile.
 //   B operand     packed weights [q][Cout][Cin] bf16 (K-major), 2-D TMA box {64, 256}.
 //   roles         warp 0: TMA producer - warp 1: tcgen05.mma issuer (warp-uniform loop, elect.sync around the issue) -
-//                 warps 2..5: epilogue.  Ring of STAGES {A,B} buffers with full/empty mbarriers; two TMEM accumulators so the
+//                 warps 2..9: epilogue (two sets of four warps split the column groups of a tile).  Ring of STAGES {A,B} buffers with full/empty mbarriers; two TMEM accumulators so the
 //                 epilogue of tile i overlaps the MMAs of tile i+1.
 //   epilogue      tcgen05.ld -> + bias -> bf16 -> a [128 px][64 ch] SWIZZLE_128B staging tile in smem -> ONE TMA store per
 //                 (quadrant, 64-channel group) through a tensor map of the strided output view {co, x (stride 2), y (stride 2), n}
@@ -26,10 +26,11 @@ constexpr int T_STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;      // 48 KB
 constexpr int T_STAGES = 3;
 constexpr int T_OUT_STAGE = 128 * 128;                             // [128 px][64 ch] bf16
 constexpr int T_MAX_COUT = 512;
-constexpr int CONV_THREADS = 192;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = 128;                                   // one epilogue set = 4 warps = the 4 TMEM lane quadrants
+constexpr int EPI_SETS = 2;                                        // two sets split the 64-column groups of a tile between them
+constexpr int CONV_THREADS = 64 + EPI_SETS * EPI_THREADS;
 constexpr int T_AUX_BYTES = T_MAX_COUT * 4 + (2 * T_STAGES + 4) * 8 + 16;
-constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + 2 * T_OUT_STAGE + T_AUX_BYTES + 1024;
+constexpr int T_SMEM_BYTES = T_STAGES * T_STAGE_BYTES + 2 * EPI_SETS * T_OUT_STAGE + T_AUX_BYTES + 1024;
 
 struct ConvTArgs {
     int k_chunks;                  // Cin / 64
@@ -54,7 +55,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 
     // carve-up: [STAGES x {A, B}] [2 x output staging] [bias] [full STAGES] [empty STAGES] [tfull 2] [tempty 2] [tmem ptr]
     const uint32_t out_stage_base = smem_base + T_STAGES * T_STAGE_BYTES;
-    constexpr uint32_t AUX_OFF = T_STAGES * T_STAGE_BYTES + 2 * T_OUT_STAGE;
+    constexpr uint32_t AUX_OFF = T_STAGES * T_STAGE_BYTES + 2 * EPI_SETS * T_OUT_STAGE;
     float* s_bias = reinterpret_cast<float*>(smem_gen + AUX_OFF);
     const uint32_t bar_base = smem_base + AUX_OFF + T_MAX_COUT * 4;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -72,7 +73,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < T_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_THREADS / 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPI_SETS * EPI_THREADS / 32); }
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -142,12 +143,16 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
     } else {
-        // ===================================================================== epilogue (4 warps = 128 TMEM lanes)
+        // ===================================================================== epilogue: 2 sets x 4 warps.  A set covers the 128 TMEM
+        // lanes (warp % 4 = lane quadrant); set e handles the 64-column groups g = e, e + 2 of every tile with its own pair of
+        // staging buffers and its own named barrier, so the 64 KB of output per tile is converted and stored by 8 warps.
+        const int eset = (warp - 2) >> 2;
         const int quad = warp & 3;                                   // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;                            // accumulator row = input pixel within the tile
-        const int et = threadIdx.x - 64;                             // 0..127
-        if (a.bias) for (int c = et; c < a.c_out; c += EPI_THREADS) s_bias[c] = a.bias[c];
-        named_bar_sync(1, EPI_THREADS);
+        const int et = (threadIdx.x - 64) & (EPI_THREADS - 1);       // 0..127 within the set
+        const int bar_id = 1 + eset;
+        if (a.bias) for (int c = threadIdx.x - 64; c < a.c_out; c += EPI_SETS * EPI_THREADS) s_bias[c] = a.bias[c];
+        named_bar_sync(3, EPI_SETS * EPI_THREADS);
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -161,14 +166,14 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * T_BLOCK_N);
 #pragma unroll 1
-            for (int g = 0; g < T_BLOCK_N / 64; ++g) {               // one 64-column group = one (quadrant, 64-channel) store
+            for (int g = eset; g < T_BLOCK_N / 64; g += EPI_SETS) {  // one 64-column group = one (quadrant, 64-channel) store
                 const int n = n_blk * T_BLOCK_N + g * 64;
                 if (a.dgrad && n >= a.n_valid) break;                // uniform: the N block overhangs Cin
                 const int q = a.dgrad ? 0 : n / a.c_out;             // a group never straddles a quadrant (c_out % 64 == 0)
                 const int co = n - q * a.c_out;
-                const uint32_t o_stage = out_stage_base + (store_groups & 1u) * T_OUT_STAGE;
+                const uint32_t o_stage = out_stage_base + (uint32_t)(eset * 2 + (store_groups & 1u)) * T_OUT_STAGE;
                 if (et == 0) bulk_wait_read<1>();                    // the store that last used this buffer has read it
-                named_bar_sync(1, EPI_THREADS);
+                named_bar_sync(bar_id, EPI_THREADS);
                 const uint32_t rbase = o_stage + (uint32_t)row * 128u;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -191,7 +196,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                 }
                 fence_proxy_async();
-                named_bar_sync(1, EPI_THREADS);
+                named_bar_sync(bar_id, EPI_THREADS);
                 if (et == 0) {
                     const CUtensorMap* mo = (q == 0) ? &tmO0 : (q == 1) ? &tmO1 : (q == 2) ? &tmO2 : &tmO3;
                     tma_store_4d(mo, o_stage, co, tx * TW, ty * TH, img);
@@ -201,7 +206,7 @@ convt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));             // 4 arrivals (one per epilogue warp) free the accumulator
+            if (lane == 0) mbar_arrive(tempty_bar(acc));             // 8 arrivals (one per epilogue warp) free the accumulator
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         if (et == 0) bulk_wait<0>();                                 // smem must outlive the last bulk stores
