@@ -192,6 +192,35 @@ wgrad_reduce_kernel(const WgradArgs a) {
     }
 }
 
+// Same fold for the layers with MANY splits and a small gradient (the full-resolution levels: 148 partial tiles for a 64 x 64 x 9
+// gradient): one block per (output row m, tap, 64 columns); its 256 threads are 64 columns x 4 split groups, so the partial reads
+// are spread over 9 x 4 times more threads than above.  Split group j adds splits j, j+4, ... in ascending order and the four
+// group sums are combined in a fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_splits_kernel(const WgradArgs a) {
+    __shared__ float s_part[4][64];
+    const int all_taps = a.groups * a.taps;
+    const long long plane = (long long)a.m_pad * a.n_pad;
+    const int chunks = (a.n_total + 63) / 64;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    for (int blk = blockIdx.x; blk < a.m_total * all_taps * chunks; blk += gridDim.x) {
+        const int ch = blk % chunks;
+        const int t = (blk / chunks) % all_taps;
+        const int m = blk / (chunks * all_taps);
+        const int n = ch * 64 + tx;
+        float acc = 0.f;
+        if (n < a.n_total) {
+            const float* p = a.partial + (long long)t * plane + (long long)m * a.n_pad + n;
+            for (int s = ty; s < a.splits; s += 4) acc += p[(long long)s * all_taps * plane];
+        }
+        s_part[ty][tx] = acc;
+        __syncthreads();
+        if (ty == 0 && n < a.n_total)
+            a.out[(long long)m * a.sm + (long long)n * a.sn + a.tap_off[t]] = ((s_part[0][tx] + s_part[1][tx]) + s_part[2][tx]) + s_part[3][tx];
+        __syncthreads();
+    }
+}
+
 // MN-major SWIZZLE_128B descriptor strides, confirmed by a sweep on B200 (profiles/README.md): LBO = bytes between 64-channel
 // blocks, SBO = bytes between 8-pixel row groups; every other combination produces garbage.
 constexpr uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024;
@@ -257,8 +286,14 @@ static int launch_wgrad(const CUtensorMap& mA, const CUtensorMap* mB, WgradArgs&
     }
     ADN_LAUNCH_CHECK();
     if (args.sn != args.groups * args.taps) return ADN_ERR_ARG;          // the fold writes contiguous tap runs
-    long long rg = (long long)args.m_total * ((args.n_total + 255) / 256); const long long cap = (long long)num_sms() * 16; if (rg > cap) rg = cap;
-    wgrad_reduce_kernel<<<(int)rg, 256, 0, stream>>>(args);
+    const long long cap = (long long)num_sms() * 16;
+    if (args.splits >= 8) {
+        long long rg = (long long)args.m_total * args.groups * args.taps * ((args.n_total + 63) / 64); if (rg > cap) rg = cap;
+        wgrad_reduce_splits_kernel<<<(int)rg, 256, 0, stream>>>(args);
+    } else {
+        long long rg = (long long)args.m_total * ((args.n_total + 255) / 256); if (rg > cap) rg = cap;
+        wgrad_reduce_kernel<<<(int)rg, 256, 0, stream>>>(args);
+    }
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

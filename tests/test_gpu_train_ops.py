@@ -300,3 +300,33 @@ def test_grad_norm_and_adamw_match_torch():
         _lib.check(lib.adn_adamw_step_f32(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, nc.data_ptr(), 1e-4, 0.9, 0.999, 1e-8, 0.01,
                                           step, sp()))
         assert float((p.cpu() - pr.detach()).abs().max()) < 5e-7
+
+
+def test_pack_table_equals_individual_packs():
+    """adn_pack_weights_table_bf16 (one launch for every layer, tiled through shared memory) writes exactly what the four
+    per-tensor pack entry points write."""
+    import numpy as np
+    lib = _lib.load()
+    d = dev()
+    g = torch.Generator().manual_seed(12)
+    shapes = [(0, 128, 64), (0, 64, 192), (1, 128, 64), (0, 256, 256)]           # (kind, c_out, c_in)
+    rec = np.dtype([("w", np.uint64), ("fwd", np.uint64), ("dgrad", np.uint64), ("c_out", np.int32), ("c_in", np.int32),
+                    ("kind", np.int32), ("pad", np.int32)])
+    keep, rows, refs = [], [], []
+    for kind, co, ci in shapes:
+        w = (torch.randn((co, ci, 3, 3) if kind == 0 else (ci, co, 2, 2), generator=g)).to(d)
+        n = w.numel()
+        fwd, dg = torch.zeros(n, dtype=torch.bfloat16, device=d), torch.zeros(n, dtype=torch.bfloat16, device=d)
+        rf, rd = torch.zeros_like(fwd), torch.zeros_like(dg)
+        if kind == 0:
+            _lib.check(lib.adn_pack_conv3x3_weight_bf16(w.data_ptr(), co, ci, rf.data_ptr(), sp()))
+            _lib.check(lib.adn_pack_conv3x3_dgrad_weight_bf16(w.data_ptr(), co, ci, rd.data_ptr(), sp()))
+        else:
+            _lib.check(lib.adn_pack_convt2x2_weight_bf16(w.data_ptr(), ci, co, rf.data_ptr(), sp()))
+            _lib.check(lib.adn_pack_convt2x2_dgrad_weight_bf16(w.data_ptr(), ci, co, rd.data_ptr(), sp()))
+        rows.append((w.data_ptr(), fwd.data_ptr(), dg.data_ptr(), co, ci, kind, 0))
+        keep.append((w, fwd, dg)); refs.append((rf, rd))
+    table = torch.from_numpy(np.array(rows, dtype=rec).view(np.uint8).copy()).to(d)
+    _lib.check(lib.adn_pack_weights_table_bf16(table.data_ptr(), len(rows), sp()))
+    for (w, fwd, dg), (rf, rd) in zip(keep, refs):
+        assert torch.equal(fwd, rf) and torch.equal(dg, rd)
