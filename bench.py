@@ -395,6 +395,9 @@ def run_b200(args):
         net._ws = {}
         torch.cuda.empty_cache()
         train = run_train_bench(args, dev, world, rank, barrier, max_over_ranks)
+        if args.train_batch != 64:            # SURVEY 8d config 5 names both batch 16 (train.py default) and 64 per GPU
+            big = run_train_bench(args, dev, world, rank, barrier, max_over_ranks, batch_override=64)
+            train["batch64"] = {k: big[k] for k in ("ms_per_step", "pairs_per_s", "e2e_pairs_per_s", "tflops")}
 
     if rank == 0:
         line = {
@@ -425,7 +428,7 @@ def run_b200(args):
     return 0
 
 
-def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
+def run_train_bench(args, dev, world, rank, barrier, max_over_ranks, batch_override=None):
     """BASELINE config 5: the train.py:65-72 step (train-mode forward + CombinedPerceptualLoss + backward + clip + AdamW) on
     synthetic (B,1,256,64) spectrogram pairs after the loader's float16 round trip, data-parallel over the ranks (one NCCL
     all-reduce of the flat 31 M-element gradient per step).  Returns the `train_step` object of the JSON line."""
@@ -435,7 +438,7 @@ def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
     from audiodenoiser_b200.model import UNet
     from audiodenoiser_b200.training import TrainEngine
 
-    b = args.train_batch
+    b = args.train_batch if batch_override is None else batch_override
     net = UNet()
     net.load_state_dict(seeded_state_dict(7))
     eng = TrainEngine(net, lr=1e-4, device=dev)
@@ -476,7 +479,7 @@ def run_train_bench(args, dev, world, rank, barrier, max_over_ranks):
            "e2e_pairs_per_s": b * world / (ms_e2e * 1e-3), "tflops": flops / (ms_dev * 1e-3) / 1e12, "kernel_launches_per_step": launches, "cuda_graph": True,
            "h2d_bytes_per_step": 2 * b * 256 * 64 * 4 * world, "d2h_bytes_per_step": 16 * world,
            "losses_after_warmup": losses, "parallelism": f"ddp{world}: one all_reduce(AVG) of the flat fp32 gradient (31.04 M elements) per step" if world > 1 else "single GPU"}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and batch_override is None:
         from oracle.train_oracle import TrainOracle
         torch.set_num_threads(os.cpu_count() or 1)
         nb = min(b, 4)
