@@ -31,6 +31,8 @@ SIGNATURES = {
     "adn_random_phasor_c64": (c_int, [c_uint64, c_int64, c_int64, P, P]),
     "adn_stft_mag_host_f32": (c_int, [P, c_int64, c_int64, c_int, P]),
     "adn_istft_ola_host_f32": (c_int, [P, P, c_uint64, c_int64, c_int64, P]),
+    "adn_mix_noise_snr_f32": (c_int, [P, P, c_int64, c_int64, c_float, P, P]),
+    "adn_mix_noise_cancel_f32": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_float, P, P]),
     "adn_pack_conv3x3_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
     "adn_pack_convt2x2_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
     "adn_fold_bn_f32": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P]),

@@ -88,6 +88,18 @@ int adn_stft_mag_host_f32(const float* wave_host, int64_t n_clips, int64_t lengt
 int adn_istft_ola_host_f32(const float* mag_host, const float* phasor_c64_host, uint64_t seed,
                            int64_t n_clips, int64_t n_frames, float* audio_host);
 
+/* ------------------------------------------------------------------ noise synthesis
+ * add_noise of create_train_dataset.py:105-159 / create_test_dataset.py:43-133, batched: clean, noise, out are (n_clips, length)
+ * float32, contiguous.  The random draws stay with the host (the reference's RNG calls, in its order) and are passed in.
+ *   snr:    out = clip(clean + noise * clean_rms / 10^(snr_db/20) / noise_rms, -1, 1), rms = sqrt(mean(x^2) + 1e-12); noise is
+ *           dropped when noise_rms <= 1e-9 (:148-157).  "white": noise = N(0,1) samples; "urban": the tiled / cropped snippet.
+ *   cancel: block_flags (n_clips, ceil(length/block)) uint8; in every flagged block the first `half` samples become
+ *           clean + factor * clean (factor = -0.8, block = 16000, half = 8000 in the reference, :123-135), then clip. */
+int adn_mix_noise_snr_f32(const float* clean, const float* noise, int64_t n_clips, int64_t length, float snr_db, float* out,
+                          void* stream);
+int adn_mix_noise_cancel_f32(const float* clean, const unsigned char* block_flags, int64_t n_clips, int64_t length, int block,
+                             int half, float factor, float* out, void* stream);
+
 /* ------------------------------------------------------------------ UNet (code/model.py) */
 
 /* Weight packing, done once per checkpoint load (model.py:53-68 state_dict layout, fp32 on device):

@@ -51,5 +51,14 @@ for name, n, length, center in (("c2_R_4096x24000", 4096, 24000, True), ("c2_tra
             out["istft_phasor_" + name] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
             del ph
     del x, mag
+# noise mixing at the train-chunk shape: 12 algorithmic bytes per sample (clean + noise in, noisy out)
+from audiodenoiser_b200 import noise as adn_noise  # noqa: E402
+n, length = 4096, 16000
+c = torch.rand((n, length), device=dev) - 0.5
+z = torch.randn((n, length), device=dev)
+o = torch.empty_like(c)
+ms = timeit(lambda: adn_noise.mix_noise_snr_batched(c, z, 8.0, out=o))
+b = n * length * 12
+out["mix_noise_snr_4096x16000"] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
 for k, v in out.items():
     print(k, v)
