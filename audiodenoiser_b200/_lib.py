@@ -26,6 +26,7 @@ SIGNATURES = {
     "adn_device_check": (c_int, []),
     "adn_stft_num_frames": (c_int64, [c_int64, c_int]),
     "adn_stft_mag_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
+    "adn_stft_mag_crop_f16_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, c_int, c_int, P]),
     "adn_stft_complex_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
     "adn_istft_ola_f32": (c_int, [P, P, c_int, c_uint64, c_int64, c_int64, P, P]),
     "adn_random_phasor_c64": (c_int, [c_uint64, c_int64, c_int64, P, P]),

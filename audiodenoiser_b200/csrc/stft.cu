@@ -86,10 +86,12 @@ __device__ __forceinline__ void stft_stage(float* buf, const float* __restrict__
     }
 }
 
-template <bool COMPLEX_OUT>
+// CROP: additionally (or only, when out == nullptr) emit the training tensor of SpectrogramDataset (data_loader.py:41-72): the
+// magnitudes rounded through float16 and cropped to (f_out, t_out), as a second output of the same pass.
+template <bool COMPLEX_OUT, bool CROP>
 __global__ void __launch_bounds__(STFT_THREADS, 2)
 stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long long clip_stride, int center,
-            int n_frames, int tiles_per_clip, float* __restrict__ out) {
+            int n_frames, int tiles_per_clip, float* __restrict__ out, float* __restrict__ crop, int f_out, int t_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* const samples0 = reinterpret_cast<float*>(smem_raw);
     float* const samples1 = reinterpret_cast<float*>(smem_raw + ST_SAMPLES_BYTES);
@@ -245,15 +247,25 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
                 ma[k2] = sqrt_approx(fmaf(A[k2].x, A[k2].x, A[k2].y * A[k2].y));
                 mb[k2] = sqrt_approx(fmaf(B[k2].x, B[k2].x, B[k2].y * B[k2].y));
             }
-            if (live) {
-                if (w == 0) {
-                    __stcs(row_ptr(pa, s16, 16), fabsf(A[0].y));
-                    ma[0] = fabsf(A[0].x);
-                }
+            if (w == 0) ma[0] = fabsf(A[0].x);
+            if (live && (!CROP || out != nullptr)) {
+                if (w == 0) __stcs(row_ptr(pa, s16, 16), fabsf(A[0].y));
 #pragma unroll
                 for (int k2 = 0; k2 < 16; ++k2) {
                     __stcs(row_ptr(pa, s16, k2), ma[k2]);
                     __stcs(row_ptr(pb, s16, k2), mb[k2]);
+                }
+            }
+            if (CROP) {
+                const int tf = cur_t0 + lane;
+                if (live && tf < t_out) {
+                    float* const cp = crop + (long long)cur_clip * f_out * t_out + tf;
+                    if (w == 0 && 256 < f_out) cp[256 * t_out] = __half2float(__float2half_rn(fabsf(A[0].y)));
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        if (a + 16 * k2 < f_out) cp[(a + 16 * k2) * t_out] = __half2float(__float2half_rn(ma[k2]));
+                        if (b + 16 * k2 < f_out) cp[(b + 16 * k2) * t_out] = __half2float(__float2half_rn(mb[k2]));
+                    }
                 }
             }
         }
@@ -261,27 +273,32 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
     cp_async_wait_all();
 }
 
-template <bool COMPLEX_OUT>
+template <bool COMPLEX_OUT, bool CROP>
 static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center, float* out,
-                       cudaStream_t stream) {
+                       float* crop, int f_out, int t_out, cudaStream_t stream) {
     if (n_clips < 0 || length < 0 || clip_stride < length) return ADN_ERR_ARG;
     const int64_t T = adn_stft_num_frames(length, center);
     if (T < 0) return ADN_ERR_SHORT;
     if (n_clips == 0) return ADN_OK;
-    if ((!wave && length > 0) || !out) return ADN_ERR_ARG;      // an empty centred clip still yields one zero frame
+    if ((!wave && length > 0) || (!out && !CROP)) return ADN_ERR_ARG;      // an empty centred clip still yields one zero frame
+    if (CROP && (!crop || f_out <= 0 || t_out <= 0)) return ADN_ERR_ARG;
     if (length >= ((int64_t)1 << 30) || T * ADN_N_BINS >= ((int64_t)1 << 31)) return ADN_ERR_ARG;   // 32-bit per-clip offsets
     int st = check_device();
     if (st != ADN_OK) return st;
-    const int tiles_per_clip = (int)((T + TF - 1) / TF);
+    // without the full-magnitude output only the frames that survive the crop are transformed
+    const int64_t frames_needed = (CROP && !out) ? (T < t_out ? T : (int64_t)t_out) : T;
+    const int tiles_per_clip = (int)((frames_needed + TF - 1) / TF);
     const long long total = (long long)n_clips * tiles_per_clip;
     if (total >= ((int64_t)1 << 31) - 4096) return ADN_ERR_ARG;
+    if (CROP && (T < t_out || ADN_N_BINS < f_out))                         // zero padding of data_loader.py:54-72
+        ADN_CUDA_TRY(cudaMemsetAsync(crop, 0, (size_t)n_clips * f_out * t_out * sizeof(float), stream));
     const size_t smem = ST_SMEM_BYTES;
-    auto kern = stft_kernel<COMPLEX_OUT>;
+    auto kern = stft_kernel<COMPLEX_OUT, CROP>;
     static unsigned char smem_set[64] = {0};
     ADN_CUDA_TRY(ensure_dyn_smem(kern, (int)smem, smem_set));
     const long long max_grid = (long long)num_sms() * 2;         // persistent: 2 resident CTAs per SM loop over the tiles
     const int grid = (int)(total < max_grid ? total : max_grid);
-    kern<<<grid, STFT_THREADS, smem, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, tiles_per_clip, out);
+    kern<<<grid, STFT_THREADS, smem, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, tiles_per_clip, out, crop, f_out, t_out);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
@@ -297,10 +314,15 @@ extern "C" int64_t adn_stft_num_frames(int64_t length, int center) {
 
 extern "C" int adn_stft_mag_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center,
                                 float* mag, void* stream) {
-    return adn::launch_stft<false>(wave, n_clips, length, clip_stride, center, mag, (cudaStream_t)stream);
+    return adn::launch_stft<false, false>(wave, n_clips, length, clip_stride, center, mag, nullptr, 0, 0, (cudaStream_t)stream);
 }
 
 extern "C" int adn_stft_complex_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center,
                                     float* spec_c64, void* stream) {
-    return adn::launch_stft<true>(wave, n_clips, length, clip_stride, center, spec_c64, (cudaStream_t)stream);
+    return adn::launch_stft<true, false>(wave, n_clips, length, clip_stride, center, spec_c64, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int adn_stft_mag_crop_f16_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center, float* mag,
+                                         float* crop, int f_out, int t_out, void* stream) {
+    return adn::launch_stft<false, true>(wave, n_clips, length, clip_stride, center, mag, crop, f_out, t_out, (cudaStream_t)stream);
 }

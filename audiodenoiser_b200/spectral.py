@@ -53,6 +53,25 @@ def stft_mag_batched(wave, center: bool = True, out=None):
     return out
 
 
+def stft_mag_train_batched(wave, center: bool = False, target_size=(256, 64), with_mag: bool = False):
+    """(N, L) float32 CUDA -> the training tensor of SpectrogramDataset.__getitem__ (data_loader.py:37-72), (N, 1, 256, 64)
+    float32: |STFT| rounded through float16 and zero-padded / cropped to ``target_size``, produced by the STFT kernel itself.
+    ``with_mag=True`` also returns the full (N, 257, T) magnitudes (the .npy the reference saves, create_train_dataset.py:251-254);
+    without it only the frames that survive the crop are transformed."""
+    torch, wave = _check_wave(wave)
+    n, length = wave.shape
+    t = num_frames(length, center)
+    f_out, t_out = int(target_size[0]), int(target_size[1])
+    crop = torch.empty((n, 1, f_out, t_out), dtype=torch.float32, device=wave.device)
+    mag = torch.empty((n, N_BINS, t), dtype=torch.float32, device=wave.device) if with_mag else None
+    stride = wave.stride(0) if n > 1 else max(length, 1)
+    with torch.cuda.device(wave.device):
+        st = _lib.load().adn_stft_mag_crop_f16_f32(wave.data_ptr(), n, length, stride, int(bool(center)), mag.data_ptr() if with_mag else 0,
+                                                   crop.data_ptr(), f_out, t_out, _lib.stream_ptr())
+    _lib.check(st, "adn_stft_mag_crop_f16_f32")
+    return (crop, mag) if with_mag else crop
+
+
 def stft_complex_batched(wave, center: bool = True):
     """(N, L) float32 CUDA -> (N, 257, T) complex64 STFT (librosa.stft at test.py:41)."""
     torch, wave = _check_wave(wave)

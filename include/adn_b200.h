@@ -65,6 +65,12 @@ int64_t adn_stft_num_frames(int64_t length, int center);
 int adn_stft_mag_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center,
                      float* mag, void* stream);
 
+/* |STFT| with the SpectrogramDataset transform (data_loader.py:41-72: float32 -> float16 -> float32, zero-pad / crop to
+ * (f_out, t_out)) as a second output of the same pass: crop (n_clips, f_out, t_out) float32.  mag may be NULL,
+ * in which case only the frames that survive the crop are transformed (the training-tensor path: waveform -> (256,64)). */
+int adn_stft_mag_crop_f16_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center, float* mag,
+                              float* crop, int f_out, int t_out, void* stream);
+
 /* Complex STFT (same framing), out (n_clips,257,T) complex64.  Replaces librosa.stft at test.py:41. */
 int adn_stft_complex_f32(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center,
                          float* spec_c64, void* stream);

@@ -51,3 +51,21 @@ def test_dataset_pairs_and_items(tmp_path):
     (tmp_path / "clean_extra.npy").write_bytes(b"")
     with pytest.raises(AssertionError):
         SpectrogramDataset(str(tmp_path))
+
+
+@pytest.mark.parametrize("length,center", [(16000, False), (24000, True), (4000, False), (8100, True)])
+def test_stft_second_output_is_the_loader_transform(length, center):
+    """the STFT kernel's second output == SpectrogramDataset's transform (float16 round trip, crop / zero-pad
+    to (256, 64), data_loader.py:41-72) of its own magnitudes, bit for bit -- with and without the full-magnitude output."""
+    from audiodenoiser_b200 import spectral, synth
+    x = torch.from_numpy(np.stack([synth.make_clip(i, "R")[:length] for i in range(3)])).to(torch.device("cuda", 0))
+    mag = spectral.stft_mag_batched(x, center)
+    crop, mag2 = spectral.stft_mag_train_batched(x, center, with_mag=True)
+    only = spectral.stft_mag_train_batched(x, center)
+    assert torch.equal(mag2, mag)
+    ref = np.zeros((3, 1, 256, 64), np.float32)
+    m = mag.cpu().numpy().astype(np.float16).astype(np.float32)
+    f, t = min(256, m.shape[1]), min(64, m.shape[2])
+    ref[:, 0, :f, :t] = m[:, :f, :t]
+    assert crop.shape == (3, 1, 256, 64)
+    assert np.array_equal(crop.cpu().numpy(), ref) and np.array_equal(only.cpu().numpy(), ref)
