@@ -35,6 +35,22 @@ def _align(n: int, a: int = 64) -> int:
     return (n + a - 1) // a * a
 
 
+def flat_layout():
+    """{key: (offset, numel, shape)} of every trainable tensor in state_dict order, and the padded total (in floats): the
+    layout of the engine's flat parameter / gradient / moment buffers.  Slices start on 64-float (256-byte) boundaries."""
+    offsets: "OrderedDict[str, tuple]" = OrderedDict()
+    off = 0
+    for key, (shape, _dt) in state_dict_spec().items():
+        if key.rsplit(".", 1)[1] in _BUFFER_LEAVES:
+            continue
+        numel = 1
+        for s in shape:
+            numel *= s
+        offsets[key] = (off, numel, tuple(shape))
+        off += _align(numel)
+    return offsets, off
+
+
 class TrainEngine:
     """train.py:65-72 for ``audiodenoiser_b200.model.UNet``; AdamW defaults are torch's (train.py:124 passes only lr)."""
 
@@ -51,17 +67,7 @@ class TrainEngine:
         dev = self.device
 
         # ---- flat fp32 parameter / gradient / moment buffers in state_dict order; 256-byte aligned slices
-        spec = state_dict_spec()
-        self.offsets: "OrderedDict[str, tuple]" = OrderedDict()
-        off = 0
-        for key, (shape, _dt) in spec.items():
-            if key.rsplit(".", 1)[1] in _BUFFER_LEAVES:
-                continue
-            numel = 1
-            for s in shape:
-                numel *= s
-            self.offsets[key] = (off, numel, tuple(shape))
-            off += _align(numel)
+        self.offsets, off = flat_layout()
         self.numel = off
         self.P = torch.zeros(off, dtype=torch.float32, device=dev)
         self.G = torch.zeros(off, dtype=torch.float32, device=dev)

@@ -241,7 +241,6 @@ def run_b200(args):
         host_batches.append(torch.from_numpy(np.stack(noisy)[idx] * gain).pin_memory())
         clean_mags.append(spectral.stft_mag_batched(torch.from_numpy(np.stack(clean)[idx] * gain).to(dev), True))
     dev_batches = [h.to(dev) for h in host_batches]
-    host_out = torch.empty((batch, n_out), dtype=torch.float32).pin_memory()
     n_total = batch * n_gpus
     torch.cuda.synchronize()
 
@@ -314,7 +313,7 @@ def run_b200(args):
 
     # ---- per-kernel figures, eager mode with CUDA events around every launch (same stream as the launches)
     kernels, roofline, launches_per_step = {}, None, None
-    if rank == 0 or True:
+    if True:
         net.profile = []
         eager = Denoiser(net, center=True, seed=1234 + rank, use_graph=False)
         reps = max(2, min(args.steps, 5))

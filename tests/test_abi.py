@@ -37,7 +37,8 @@ def test_every_entry_point_cites_the_reference():
     """Each compute entry point names the reference call site it replaces (file:line)."""
     text = open(HEADER).read()
     for cite in ("create_train_dataset.py:162-174", "create_test_dataset.py:35-41", "test.py:36-37,40,48", "model.py:11-16",
-                 "model.py:38,43", "model.py:68,93", "data_loader.py:37-72"):
+                 "model.py:38,43", "model.py:68,93", "data_loader.py:37-72", "train.py:65-72", "train.py:70", "loss.py:83-95",
+                 "create_train_dataset.py:105-159"):
         assert cite in text, cite
 
 
@@ -83,3 +84,45 @@ def test_product_path_raises_without_a_gpu():
     net = model.UNet().eval()
     with pytest.raises(_lib.AdnError):
         net(torch.zeros(1, 1, 32, 32))
+    # the training step, the loss, the noise mixing and the fused loader transform have no CPU path either
+    from audiodenoiser_b200 import create_train_dataset, loss, training
+    with pytest.raises(_lib.AdnError):
+        training.TrainEngine(model.UNet())
+    with pytest.raises(_lib.AdnError):
+        net.train()(torch.zeros(2, 1, 32, 32))
+    with pytest.raises(_lib.AdnError):
+        loss.CombinedPerceptualLoss()(torch.zeros(1, 1, 64, 64), torch.zeros(1, 1, 64, 64))
+    with pytest.raises(_lib.AdnError):
+        create_train_dataset.add_noise(np.zeros(16000, np.float32), None, "white")
+    with pytest.raises(_lib.AdnError):
+        spectral.stft_mag_train_batched(torch.zeros(1, 16000))
+
+
+def test_training_entry_points_reject_bad_arguments_before_any_device_work():
+    lib = _lib.load()
+    assert lib.adn_train_workspace_bytes() > 0 and lib.adn_wgrad_workspace_bytes() > 0
+    assert lib.adn_loss_backward_workspace_bytes(4, 256, 64) > 0 and lib.adn_loss_backward_workspace_bytes(-1, 256, 64) == -1
+    assert lib.adn_bn_relu_apply_bf16(None, None, None, 10, 64, None, None) == 1
+    assert lib.adn_maxpool2x2_backward_add_bf16(None, None, None, 0, 1, 4, 4, 64, None, None) == 1
+    assert lib.adn_adamw_step_f32(None, None, None, None, 0, None, 1e-4, 0.9, 0.999, 1e-8, 0.01, 1, None) == 1
+    assert lib.adn_grad_norm_f32(None, 0, 1.0, None, None, None) == 1
+    assert lib.adn_mix_noise_snr_f32(None, None, 0, 16000, 8.0, None, None) == 0        # empty batch
+    assert lib.adn_mix_noise_snr_f32(None, None, 2, 16000, 8.0, None, None) == 1
+    assert lib.adn_pack_weights_table_bf16(None, 3, None) == 1
+
+
+def test_flat_parameter_layout_is_the_state_dict_order():
+    """TrainEngine's flat buffers: every trainable tensor of the 136-key state_dict, in order, each slice 256-byte aligned."""
+    from audiodenoiser_b200.checkpoint import state_dict_spec
+    from audiodenoiser_b200.training import flat_layout
+    offsets, total = flat_layout()
+    spec = state_dict_spec()
+    trainable = [k for k in spec if not k.endswith(("running_mean", "running_var", "num_batches_tracked"))]
+    assert list(offsets) == trainable and len(trainable) == 82
+    end = 0
+    n_params = 0
+    for k, (off, numel, shape) in offsets.items():
+        assert off % 64 == 0 and off >= end and tuple(shape) == tuple(spec[k][0])
+        end = off + numel
+        n_params += numel
+    assert n_params == 31042369 and total >= end and total % 64 == 0
