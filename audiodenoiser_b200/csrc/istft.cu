@@ -56,7 +56,9 @@ __device__ __forceinline__ const T* is_row_ptr(const T* base, int stride_bytes, 
     return reinterpret_cast<const T*>(r);
 }
 
-// MODE 0: spec = mag * phasor ; MODE 1: spec = phasor array itself (complex spectrogram) ; MODE 2: mag * random phasor
+// MODE 0: spec = mag * phasor ; MODE 1: spec = phasor array itself (complex spectrogram) ; MODE 2: mag * random phasor ;
+// MODE 3: spec = mag * C / |C| for an arbitrary complex array C (the phase of another spectrogram, e.g. the noisy input's:
+//         SURVEY 8f row 4, an opt-in that is NOT what the reference computes)
 template <int MODE>
 __global__ void __launch_bounds__(IS_THREADS, 2)
 istft_kernel(const float* __restrict__ mag, const float2* __restrict__ ph, unsigned long long seed,
@@ -142,6 +144,12 @@ istft_kernel(const float* __restrict__ mag, const float2* __restrict__ ph, unsig
             if (MODE == 2) key = phase_key(seed, clip);
             auto spec = [&](int j, int c, int i1) -> float2 {            // raw slot j = element (c + 16 i1) * T + t
                 if (MODE == 1) return rp[j];
+                if (MODE == 3) {                                          // phase of rp[j]; a zero bin keeps phase 0
+                    const float2 q = rp[j];
+                    const float n2 = fmaf(q.x, q.x, q.y * q.y);
+                    const float s = n2 > 0.f ? rm[j] * rsqrtf(n2) : 0.f;
+                    return n2 > 0.f ? make_float2(q.x * s, q.y * s) : make_float2(rm[j], 0.f);
+                }
                 const float2 p = (MODE == 0) ? rp[j] : phasor_from_bits(phase_bits(key, (uint32_t)c, (uint32_t)i1, (uint32_t)n_frames, (uint32_t)tc));
                 return make_float2(rm[j] * p.x, rm[j] * p.y);
             };
@@ -271,7 +279,7 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
     if (n_clips < 0 || n_frames < 1 || n_frames * ADN_N_BINS >= ((int64_t)1 << 31) / 2) return ADN_ERR_ARG;   // 32-bit per-clip byte offsets
     if (n_clips == 0 || n_frames == 1) return ADN_OK;          // hop*(T-1) = 0 samples
     if (!audio) return ADN_ERR_ARG;
-    if (spec_is_complex ? !phasor : !mag) return ADN_ERR_ARG;
+    if (spec_is_complex == 2 ? (!phasor || !mag) : spec_is_complex ? !phasor : !mag) return ADN_ERR_ARG;
     if ((reinterpret_cast<uintptr_t>(audio) & 15) != 0) return ADN_ERR_ARG;
     int st = check_device();
     if (st != ADN_OK) return st;
@@ -290,7 +298,8 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
         istft_kernel<MODE><<<grid, IS_THREADS, smem, stream>>>(mag, ph, (unsigned long long)seed, n_clips, (int)n_frames, \
                                                                tiles_per_clip, audio);                             \
     } while (0)
-    if (spec_is_complex) ADN_ISTFT_LAUNCH(1);
+    if (spec_is_complex == 2) ADN_ISTFT_LAUNCH(3);
+    else if (spec_is_complex) ADN_ISTFT_LAUNCH(1);
     else if (phasor) ADN_ISTFT_LAUNCH(0);
     else ADN_ISTFT_LAUNCH(2);
 #undef ADN_ISTFT_LAUNCH

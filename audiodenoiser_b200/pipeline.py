@@ -14,8 +14,13 @@ from .model import UNet
 
 
 class Denoiser:
-    def __init__(self, model: UNet, center: bool = True, seed: int = 0, use_graph: bool = True):
+    def __init__(self, model: UNet, center: bool = True, seed: int = 0, use_graph: bool = True, phase: str = "random"):
+        """phase="random" is the reference's reconstruction (test.py:36: a fresh random phase).  phase="noisy" (opt-in, SURVEY 8f
+        row 4) reuses the phase of the noisy input's STFT -- audibly better, but NOT what the reference computes."""
         _lib.require_cuda()
+        if phase not in ("random", "noisy"):
+            raise ValueError("phase must be 'random' or 'noisy'")
+        self.phase = phase
         self.model = model.eval()
         self.center = bool(center)
         self.seed = int(seed)
@@ -36,12 +41,10 @@ class Denoiser:
             if not wave.is_cuda:
                 wave = wave.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
             wave = wave.contiguous()
-            mag = spectral.stft_mag_batched(wave, self.center)
-            den = self.model(mag.unsqueeze(1)).squeeze(1)
-            audio = spectral.istft_batched(den, phasor, seed=self.seed)
+            audio, mag, den = self._run(wave, phasor)
             return (audio, mag, den) if return_spectrograms else audio
         dev = wave.device if wave.is_cuda else torch.device("cuda", torch.cuda.current_device())
-        key = (tuple(wave.shape), str(dev), phasor is not None, self.model._version_key(dev))
+        key = (tuple(wave.shape), str(dev), phasor is not None, self.phase, self.model._version_key(dev))
         g = self._graphs.get(key)
         if g is None:
             g = self._capture(wave.to(dev), phasor)
@@ -55,6 +58,16 @@ class Denoiser:
             return g["audio"], g["mag"], g["den"]
         return g["audio"]
 
+    def _run(self, wave, phasor):
+        if self.phase == "noisy" and phasor is None:
+            spec = spectral.stft_complex_batched(wave, self.center)
+            mag = spec.abs()
+            den = self.model(mag.unsqueeze(1)).squeeze(1)
+            return spectral.istft_batched(den, phase_from=spec), mag, den
+        mag = spectral.stft_mag_batched(wave, self.center)
+        den = self.model(mag.unsqueeze(1)).squeeze(1)
+        return spectral.istft_batched(den, phasor, seed=self.seed), mag, den
+
     def _capture(self, wave, phasor):
         dev = wave.device
         static_wave = wave.contiguous().clone()
@@ -65,16 +78,12 @@ class Denoiser:
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
                 for _ in range(2):
-                    mag = spectral.stft_mag_batched(static_wave, self.center)
-                    den = self.model(mag.unsqueeze(1)).squeeze(1)
-                    audio = spectral.istft_batched(den, static_ph, seed=self.seed)
+                    audio, mag, den = self._run(static_wave, static_ph)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                mag = spectral.stft_mag_batched(static_wave, self.center)
-                den = self.model(mag.unsqueeze(1)).squeeze(1)
-                audio = spectral.istft_batched(den, static_ph, seed=self.seed)
+                audio, mag, den = self._run(static_wave, static_ph)
         # the graph holds raw pointers into the model's packed weights and activation workspace: keep them alive here even if
         # the model later repacks (new checkpoint) or switches to another input shape
         keep = (self.model._packed, dict(self.model._ws))

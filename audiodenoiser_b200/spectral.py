@@ -85,11 +85,13 @@ def stft_complex_batched(wave, center: bool = True):
     return out
 
 
-def istft_batched(mag, phasor=None, seed: int = 0, out=None):
+def istft_batched(mag, phasor=None, seed: int = 0, out=None, phase_from=None):
     """Inverse STFT + overlap-add: (N,257,T) magnitude x (N,257,T) complex64 unit phasor -> (N, 128*(T-1)) float32.
 
     ``phasor=None`` draws a uniform random phase on the device from ``seed`` (test.py:36 uses the unseeded numpy RNG).
-    A complex ``mag`` is taken as the complex spectrogram itself (librosa.istft at test.py:40)."""
+    A complex ``mag`` is taken as the complex spectrogram itself (librosa.istft at test.py:40).
+    ``phase_from`` (opt-in, NOT the reference's behaviour): a complex (N,257,T) spectrogram whose phase is used, i.e. the
+    kernel inverts ``mag * phase_from / |phase_from|`` (denoised magnitude + noisy phase)."""
     torch = _lib.require_cuda()
     if not isinstance(mag, torch.Tensor) or not mag.is_cuda:
         raise _lib.AdnError("expected a CUDA tensor (no CPU fallback)")
@@ -99,7 +101,18 @@ def istft_batched(mag, phasor=None, seed: int = 0, out=None):
         raise ValueError("spectrogram must be (257, T) or (N, 257, T)")
     n, _, t = mag.shape
     is_complex = mag.is_complex()
-    if is_complex:
+    mode = 1 if is_complex else 0
+    if phase_from is not None:
+        if is_complex or phasor is not None:
+            raise ValueError("phase_from needs a real magnitude and no phasor")
+        if phase_from.dim() == 2:
+            phase_from = phase_from.unsqueeze(0)
+        if tuple(phase_from.shape) != tuple(mag.shape) or not phase_from.is_complex():
+            raise ValueError("phase_from must be a complex tensor of the magnitude's shape")
+        mag = mag.float().contiguous()
+        phase_from = phase_from.to(device=mag.device, dtype=torch.complex64).contiguous()
+        mag_ptr, ph_ptr, mode = mag.data_ptr(), phase_from.data_ptr(), 2
+    elif is_complex:
         if phasor is not None:
             raise ValueError("phasor must be None when the spectrogram is complex")
         spec = mag.to(torch.complex64).contiguous()
@@ -122,7 +135,7 @@ def istft_batched(mag, phasor=None, seed: int = 0, out=None):
     elif tuple(out.shape) != (n, n_out) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be a contiguous float32 (N, 128*(T-1)) tensor")
     with torch.cuda.device(mag.device):
-        st = _lib.load().adn_istft_ola_f32(mag_ptr, ph_ptr, int(is_complex), int(seed) & 0xFFFFFFFFFFFFFFFF, n, t,
+        st = _lib.load().adn_istft_ola_f32(mag_ptr, ph_ptr, mode, int(seed) & 0xFFFFFFFFFFFFFFFF, n, t,
                                            out.data_ptr(), _lib.stream_ptr())
     _lib.check(st, "adn_istft_ola_f32")
     return out

@@ -80,7 +80,9 @@ int adn_stft_complex_f32(const float* wave, int64_t n_clips, int64_t length, int
  * (test.py:36-37,40,48).  Atomic-free and deterministic: every output sample adds its <=4 frame contributions in
  * ascending frame order.  phasor may be NULL: a unit phasor with uniform random phase is then generated on the
  * device from `seed` (the reference draws it from the unseeded numpy RNG, test.py:36).
- * mag may be NULL when `spec_is_complex` != 0, in which case phasor holds the complex spectrogram itself. */
+ * spec_is_complex == 1: mag may be NULL and phasor holds the complex spectrogram itself (librosa.istft at test.py:40).
+ * spec_is_complex == 2 (opt-in, not what the reference computes): phasor holds an arbitrary complex
+ * spectrogram C and the kernel inverts mag * C / |C| -- e.g. the denoised magnitude with the NOISY input's phase. */
 int adn_istft_ola_f32(const float* mag, const float* phasor_c64, int spec_is_complex, uint64_t seed,
                       int64_t n_clips, int64_t n_frames, float* audio, void* stream);
 

@@ -73,3 +73,20 @@ def test_stream_host_batches_equals_sequential(net):
     for o, r, s in zip(outs, ref, stats):
         assert torch.equal(o, r)
         assert float(s) == float(r[0, 0])
+
+
+def test_noisy_phase_reconstruction_opt_in(net):
+    """SURVEY 8f row 4 (opt-in, not the reference's behaviour): denoised magnitude + the noisy input's phase.  The kernel
+    inverts mag * C / |C|; with mag = |C| that is istft(C), i.e. the input itself."""
+    from audiodenoiser_b200 import spectral
+    x = torch.from_numpy(np.stack([synth.make_clip(i, "R") for i in range(2)])).to(dev())
+    spec = spectral.stft_complex_batched(x, True)
+    same = spectral.istft_batched(spec.abs(), phase_from=spec)
+    assert float((same - x[:, :same.shape[1]]).abs().max()) <= 5e-6
+    ref = spectral.istft_batched(spec.abs() * 0.5, torch.polar(torch.ones_like(spec.abs()), torch.angle(spec)))
+    got = spectral.istft_batched(spec.abs() * 0.5, phase_from=spec)
+    assert float((got - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    a = Denoiser(net, phase="noisy", use_graph=False).denoise(x)
+    b = Denoiser(net, phase="noisy", use_graph=True).denoise(x)
+    assert a.shape == (2, 23936) and torch.equal(a, b)
+    assert not torch.equal(a, Denoiser(net, seed=1, use_graph=False).denoise(x))
