@@ -117,19 +117,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc_mn(BN);
+        // The taps of a group sit in consecutive 8 KB sub-tiles, i.e. they ARE one MN-major operand with taps*BN columns (LBO = 8 KB
+        // between 64-column blocks): one UMMA per k-slice covers up to 256 columns (BN = 64: all 3 or 4 taps, N = 192 / 256;
+        // BN = 128: two taps, then the rest) instead of one N = BN instruction per tap -- per-MMA smem operand traffic drops from
+        // A + B to A + B over 3-4x the work, which took the 64-wide layers off the shared-memory read limit.
+        const int taps_first = (a.taps * BN <= 256) ? a.taps : 256 / BN;
+        const int taps_rest = a.taps - taps_first;
+        const uint32_t idesc0 = make_idesc_mn(taps_first * BN);
+        const uint32_t idesc1 = make_idesc_mn(taps_rest > 0 ? taps_rest * BN : BN);
         int stage = 0; uint32_t phase = 0;
         for (int kt = kt0; kt < kt1; ++kt) {
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
             const uint32_t sa = smem_base + (uint32_t)stage * stage_bytes;
             if (elect_one()) {
-                for (int t = 0; t < a.taps; ++t) {
-                    const uint32_t sb = sa + (uint32_t)(2 + t * NSUB) * WG_SUB;
+                const uint32_t sb0 = sa + 2u * WG_SUB;
+                const uint32_t sb1 = sb0 + (uint32_t)(taps_first * NSUB) * WG_SUB;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)              // UMMA_K = 16 pixels = 16 rows of 128 B
-                        umma_bf16(tmem_base + (uint32_t)(t * BN), make_mn_sw128_desc(sa + k * 2048, a.lbo, a.sbo),
-                                  make_mn_sw128_desc(sb + k * 2048, a.lbo, a.sbo), idesc, (kt > kt0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {                // UMMA_K = 16 pixels = 16 rows of 128 B
+                    const uint64_t da = make_mn_sw128_desc(sa + k * 2048, a.lbo, a.sbo);
+                    const uint32_t accf = (kt > kt0 || k > 0) ? 1u : 0u;
+                    umma_bf16(tmem_base, da, make_mn_sw128_desc(sb0 + k * 2048, a.lbo, a.sbo), idesc0, accf);
+                    if (taps_rest > 0)
+                        umma_bf16(tmem_base + (uint32_t)(taps_first * BN), da, make_mn_sw128_desc(sb1 + k * 2048, a.lbo, a.sbo), idesc1, accf);
                 }
                 umma_commit(empty_bar(stage));
             }
