@@ -120,62 +120,92 @@ __global__ void fold_bn_kernel(const float* __restrict__ conv_bias, const float*
 // ------------------------------------------------------------------------------------------------ first layer
 // (n,1,h,w) fp32 -> conv3x3 pad 1 (64 filters, fp32 math) -> folded BN -> ReLU -> NHWC bf16.
 // HBM-bound on the 128 B/pixel it writes (algorithmic: 4 B in + 128 B out per pixel).  8 lanes per pixel group, 8 output
-// channels per lane, 4 consecutive pixels per lane with a sliding 3x6 input window: 18 independent loads are in flight per
-// thread, every weight vector read from shared memory feeds 4 pixels (32 FMAs per 2 LDS.128), and each store instruction of
-// a warp writes four complete 128-byte lines.
-constexpr int C1_RUN = 4;
-__global__ void __launch_bounds__(256)
-conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, const float* __restrict__ weight,
+// channels per lane, C1_RUN consecutive pixels per lane with a sliding 3x(C1_RUN+2) input window.  What limits it below the
+// HBM floor is L1 wavefronts, not FMA issue (ncu r1i: l1tex 97 %): a weight LDS.128 costs one wavefront per quarter warp, so
+// (a) the weights are laid out [tap][half][lane][4] -- the 8 lanes of a quarter warp read one contiguous 128-byte line instead
+// of eight 16-byte pieces 32 bytes apart (2-way bank conflict) -- and (b) every weight vector feeds C1_RUN pixels (8 on wide
+// rows: 64 FFMA2 per 2 LDS.128).  Each store instruction of a warp writes four complete 128-byte lines.
+// STAGED: the block first copies its row span (+ one halo row either side, one zero column either side, ragged tail zeroed)
+// into shared memory, so the pixel loop holds no long-latency load and no column bounds check; rows_per_block / pitch come
+// from the host.  !STAGED reads the window straight from global memory (rows too wide for 45 KB of staging).
+template <int C1_RUN, bool STAGED>
+__global__ void __launch_bounds__(256, 2)
+conv3x3_c1_kernel(const float* __restrict__ x, int n, int h, int w, int rows_per_block, int pitch, const float* __restrict__ weight,
                   const float* __restrict__ scale, const float* __restrict__ shift, float relu_floor, uint4* __restrict__ out) {
-    __shared__ __align__(16) float s_w[9][64];
-    for (int i = threadIdx.x; i < 576; i += blockDim.x) s_w[i % 9][i / 9] = weight[i];   // weight[c][tap]
+    extern __shared__ __align__(16) float s_x[];            // STAGED: [rows_per_block + 2][pitch]
+    __shared__ __align__(16) float s_w[9][2][8][4];
+    for (int i = threadIdx.x; i < 576; i += blockDim.x) {                                  // weight[c][tap]
+        const int c = i / 9;
+        s_w[i % 9][(c >> 2) & 1][c >> 3][c & 3] = weight[i];
+    }
     const int cg = threadIdx.x & 7, grp = threadIdx.x >> 3;
-    float sc[8], sh[8];
+    float2 sc[4], sh[4];                                    // channel pairs: the math below is packed fp32x2 (FFMA2)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) { sc[c] = __ldg(scale + cg * 8 + c); sh[c] = __ldg(shift + cg * 8 + c); }
-    __syncthreads();
+    for (int c = 0; c < 4; ++c) {
+        sc[c] = make_float2(__ldg(scale + cg * 8 + 2 * c), __ldg(scale + cg * 8 + 2 * c + 1));
+        sh[c] = make_float2(__ldg(shift + cg * 8 + 2 * c), __ldg(shift + cg * 8 + 2 * c + 1));
+    }
+    // a block owns a contiguous span of rows and its 32 pixel groups stride through the span's (row, run) units, so the
+    // ragged last run of a row (w = 1034: two of 130) does not leave one warp with an extra pass per row
     const int n_rows = n * h;
-    for (int row = blockIdx.x; row < n_rows; row += gridDim.x) {
-        const int py = row % h;
-        const float* __restrict__ xr = x + (long long)row * w;
-        const bool rok[3] = {py > 0, true, py + 1 < h};
-        uint4* __restrict__ orow = out + (long long)row * w * 8 + cg;
-        for (int px0 = grp * C1_RUN; px0 < w; px0 += 32 * C1_RUN) {
+    const int row0 = blockIdx.x * rows_per_block;
+    const int runs_per_row = (w + C1_RUN - 1) / C1_RUN;
+    const int n_own = max(0, min(rows_per_block, n_rows - row0));
+    const int n_units = n_own * runs_per_row;
+    if (STAGED) {
+        for (int r = 0; r < n_own + 2; ++r) {
+            const int g = row0 - 1 + r;
+            const bool gok = g >= 0 && g < n_rows;
+            const float* __restrict__ src = x + (long long)g * w - 1;
+#pragma unroll 5
+            for (int j = threadIdx.x; j < pitch; j += 256) s_x[r * pitch + j] = (gok && j >= 1 && j <= w) ? __ldg(src + j) : 0.f;
+        }
+    }
+    __syncthreads();
+    {
+        for (int u = grp; u < n_units; u += 32) {
+            const int row = row0 + u / runs_per_row;
+            const int px0 = (u % runs_per_row) * C1_RUN;
+            const int py = row % h;
+            const float* __restrict__ xr = x + (long long)row * w;
+            const bool rok[3] = {py > 0, true, py + 1 < h};
+            uint4* __restrict__ orow = out + (long long)row * w * 8 + cg;
             float v[3][C1_RUN + 2];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int i = 0; i < C1_RUN + 2; ++i) {
                     const int xx = px0 + i - 1;
-                    v[ky][i] = (rok[ky] && xx >= 0 && xx < w) ? __ldg(xr + (ky - 1) * w + xx) : 0.f;
+                    if (STAGED) v[ky][i] = rok[ky] ? s_x[(row - row0 + ky) * pitch + px0 + i] : 0.f;
+                    else        v[ky][i] = (rok[ky] && xx >= 0 && xx < w) ? __ldg(xr + (ky - 1) * w + xx) : 0.f;
                 }
-            float acc[C1_RUN][8];
+            float2 acc[C1_RUN][4];
 #pragma unroll
             for (int r = 0; r < C1_RUN; ++r)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+                for (int c = 0; c < 4; ++c) acc[r][c] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    const float4 w0 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8]);
-                    const float4 w1 = *reinterpret_cast<const float4*>(&s_w[ky * 3 + kx][cg * 8 + 4]);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_w[ky * 3 + kx][0][cg]);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_w[ky * 3 + kx][1][cg]);
+                    const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
 #pragma unroll
                     for (int r = 0; r < C1_RUN; ++r)
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(v[ky][r + kx], wv[c], acc[r][c]);
+                        for (int c = 0; c < 4; ++c) acc[r][c] = pk_fma(pk_bcast(v[ky][r + kx]), wv[c], acc[r][c]);
                 }
 #pragma unroll
             for (int r = 0; r < C1_RUN; ++r) {
                 if (px0 + r < w) {
-                    float y[8];
+                    uint32_t pk[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) y[c] = fmaxf(fmaf(acc[r][c], sc[c], sh[c]), relu_floor);
-                    uint4 o;
-                    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-                    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-                    __stcs(orow + (long long)(px0 + r) * 8, o);
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 y = pk_fma(acc[r][c], sc[c], sh[c]);
+                        pk[c] = pack_bf16x2(fmaxf(y.x, relu_floor), fmaxf(y.y, relu_floor));
+                    }
+                    __stcs(orow + (long long)(px0 + r) * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 }
             }
         }
@@ -335,11 +365,38 @@ extern "C" int adn_fold_bn_f32(const float* conv_bias, const float* gamma, const
     return ADN_OK;
 }
 
+template <int RUN>
+static void launch_c1_run(const float* x, int n, int h, int w, const float* weight, const float* scale, const float* shift,
+                          float relu_floor, uint4* out, cudaStream_t stream) {
+    const int n_rows = n * h, pitch = (w + RUN - 1) / RUN * RUN + 2;
+    const int max_rows = (45 * 1024) / (pitch * 4) - 2;                       // 48 KB default limit minus the weight table
+    if (max_rows >= 1) {
+        const int resident = num_sms() * 2;                                    // 2 CTAs of 256 threads per SM (register-limited)
+        int rows = max_rows;
+        for (int waves = 1; waves <= 64; ++waves) {                            // fewest whole waves whose span fits the staging
+            const int r = (n_rows + resident * waves - 1) / (resident * waves);
+            if (r <= max_rows) { rows = r; break; }
+        }
+        const int grid = (n_rows + rows - 1) / rows;
+        conv3x3_c1_kernel<RUN, true><<<grid, 256, (size_t)(rows + 2) * pitch * 4, stream>>>(x, n, h, w, rows, pitch, weight, scale, shift,
+                                                                                         relu_floor, out);
+    } else {
+        const int grid = grid_for((long long)n_rows * w * 8, 256);
+        conv3x3_c1_kernel<RUN, false><<<grid, 256, 0, stream>>>(x, n, h, w, (n_rows + grid - 1) / grid, 0, weight, scale, shift, relu_floor, out);
+    }
+}
+
+static void launch_c1(const float* x, int n, int h, int w, const float* weight, const float* scale, const float* shift,
+                      float relu_floor, uint4* out, cudaStream_t stream) {
+    if (w >= 512) launch_c1_run<8>(x, n, h, w, weight, scale, shift, relu_floor, out, stream);
+    else          launch_c1_run<4>(x, n, h, w, weight, scale, shift, relu_floor, out, stream);
+}
+
 extern "C" int adn_conv3x3_c1_bn_relu_bf16(const float* x, int n, int h, int w, const float* weight, const float* scale,
                                            const float* shift, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(x, n, h, w, weight, scale, shift, 0.f, (uint4*)out);
+    launch_c1(x, n, h, w, weight, scale, shift, 0.f, (uint4*)out, (cudaStream_t)stream);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
@@ -349,8 +406,7 @@ extern "C" int adn_conv3x3_c1_affine_bf16(const float* x, int n, int h, int w, c
                                           const float* shift, int relu, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    conv3x3_c1_kernel<<<grid_for((long long)n * h * w * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        x, n, h, w, weight, scale, shift, relu ? 0.f : -INFINITY, (uint4*)out);
+    launch_c1(x, n, h, w, weight, scale, shift, relu ? 0.f : -INFINITY, (uint4*)out, (cudaStream_t)stream);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

@@ -48,6 +48,31 @@ def net():
     return m
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 1, 1), (2, 3, 7), (3, 17, 64), (1, 5, 523), (2, 3, 1034), (1, 2, 12001)])
+@pytest.mark.parametrize("relu", [1, 0])
+def test_conv3x3_first_layer(n, h, w, relu):
+    """model.py:9-11 with one input channel (fp32 math, folded affine, optional ReLU -> NHWC bf16): short rows (4-pixel runs,
+    staged), wide ragged rows (8-pixel runs, staged) and rows too wide to stage (direct path)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n * 1000 + h * 10 + w)
+    x = torch.randn(n, 1, h, w, generator=g)
+    wt = torch.randn(64, 1, 3, 3, generator=g) * 0.3
+    sc = torch.rand(64, generator=g) + 0.5
+    sh = torch.randn(64, generator=g) * 0.2
+    ref = F.conv2d(x, wt, padding=1) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    xd, wd, scd, shd = x.to(dev()).contiguous(), wt.to(dev()).contiguous(), sc.to(dev()), sh.to(dev())
+    out = torch.full((n, h, w, 64), float("nan"), dtype=torch.bfloat16, device=dev())
+    _lib.check(lib.adn_conv3x3_c1_affine_bf16(xd.data_ptr(), n, h, w, wd.data_ptr(), scd.data_ptr(), shd.data_ptr(), relu,
+                                              out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = from_nhwc(out.cpu())
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item()        # one bf16 rounding of an fp32 result
+    assert nrel(got.numpy(), ref.numpy()) < 4e-3
+
+
 @pytest.mark.parametrize("n,c0,c1,co,h,w", [(2, 64, 0, 64, 20, 19), (1, 64, 0, 128, 37, 26), (2, 128, 0, 256, 9, 6),
                                             (1, 256, 256, 256, 16, 11), (2, 64, 64, 64, 33, 28), (1, 512, 0, 1024, 4, 3),
                                             (1, 512, 512, 512, 5, 7), (3, 64, 0, 64, 257, 188), (1, 64, 0, 64, 1, 1)])
