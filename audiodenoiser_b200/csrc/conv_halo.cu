@@ -33,11 +33,26 @@ constexpr int H_POOL_STAGE = 32 * 128;             // its 2x2-pooled counterpart
 
 enum { HEPI_NHWC = 0, HEPI_HEAD = 2 };
 
+// x / d for 0 <= x < 2^31 as one multiply-high and a shift (d == 1: mul = 0 marks the identity).  The four runtime integer
+// divisions per tile cost ~180 dependent instructions in every role; in the epilogue warps that was a fifth of the tile.
+struct FastDiv { uint32_t mul, shr; };
+static FastDiv make_fastdiv(int d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1) return f;
+    uint32_t k = 0; while ((1u << k) < (uint32_t)d) ++k;
+    const uint32_t p = 31 + k;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ int fast_div(int x, FastDiv f) { return f.mul ? (int)(__umulhi((uint32_t)x, f.mul) >> f.shr) : x; }
+
 struct HaloArgs {
     int c0_chunks, c1_chunks;
     int n_img, H, W;
     int tiles_x, tiles_y;
     int c_out, n_blocks, num_tiles;
+    FastDiv div_nb, div_tpi, div_tx;   // by n_blocks, tiles_x * tiles_y, tiles_x: the per-tile index split costs 2 instructions
     int epi;
     int a_stages, b_slots, b_resident;
     float relu_floor;              // 0 = ReLU, -inf = no activation (train-mode pre-BN output, dgrad)
@@ -123,7 +138,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const int work_total = PAIR ? ((num_m + 1) / 2) * a.n_blocks : a.num_tiles;
     const int work_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int work_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-    auto tile_m = [&](int w) { return PAIR ? 2 * (w / a.n_blocks) + (int)cta_rank : w / a.n_blocks; };
+    auto tile_m = [&](int w) { return PAIR ? 2 * fast_div(w, a.div_nb) + (int)cta_rank : fast_div(w, a.div_nb); };
+    auto tile_nblk = [&](int w) { return w - fast_div(w, a.div_nb) * a.n_blocks; };
     // full barriers live in the leader CTA; a peer's TMA completes its bytes there
     auto full_a_sig = [&](int s) { return PAIR ? mapa_shared(full_a(s), 0) : full_a(s); };
     auto full_b_sig = [&](int s) { return PAIR ? mapa_shared(full_b(s), 0) : full_b(s); };
@@ -134,9 +150,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             int stage = 0; uint32_t phase = 0;
             for (int w = work_first; w < work_total; w += work_step) {
                 const int m = tile_m(w);
-                const int img = m / tiles_per_img;                // m >= num_m (odd tail of a pair): img == n_img -> all zeros
+                const int img = fast_div(m, a.div_tpi);           // m >= num_m (odd tail of a pair): img == n_img -> all zeros
                 const int rem = m - img * tiles_per_img;
-                const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+                const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
                 const int x0 = tx * H_TW - 1, y0 = ty * H_TH - 1;
                 for (int ch = 0; ch < chunks; ++ch) {
                     mbar_wait(empty_a(stage), phase ^ 1u);
@@ -166,7 +182,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             } else {
                 int slot = 0; uint32_t phase = 0;
                 for (int w = work_first; w < work_total; w += work_step) {
-                    const int n_blk = w % a.n_blocks;
+                    const int n_blk = tile_nblk(w);
                     for (int ch = 0; ch < chunks; ++ch)
                         for (int tap = 0; tap < 9; ++tap) {
                             mbar_wait(empty_b(slot), phase ^ 1u);
@@ -260,15 +276,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const uint32_t tempty_sig0 = PAIR ? mapa_shared(tempty(0), 0) : tempty(0);
         const uint32_t tempty_sig1 = PAIR ? mapa_shared(tempty(1), 0) : tempty(1);
         for (int w = work_first; w < work_total; w += work_step) {
-            const int n_blk = w % a.n_blocks;
+            const int n_blk = tile_nblk(w);
             const int m = tile_m(w);
-            const int img = m / tiles_per_img;                      // == n_img for the padding tile of an odd pair
+            const int img = fast_div(m, a.div_tpi);                 // == n_img for the padding tile of an odd pair
             const int rem = m - img * tiles_per_img;
-            const int ty = rem / a.tiles_x, tx = rem - ty * a.tiles_x;
+            const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
             const int x = tx * H_TW + lx, y = ty * H_TH + ly;
             const bool valid = (x < a.W) && (y < a.H) && (m < num_m);
-            // pooled pixel owned by this lane: lanes with even (lx, ly); its 2x2 window = lanes ^1, ^8, ^9 of the same warp
-            const bool pool_writer = a.pool_out && !(lx & 1) && !(ly & 1) && (x >> 1) < Wp && (y >> 1) < Hp;
+            // the pooled pixel this lane contributes to (its 2x2 window = lanes l, l^1, l^8, l^9 of the same warp) exists
+            const bool pool_px = a.pool_out && (m < num_m) && (x >> 1) < Wp && (y >> 1) < Hp;
 
             const float* t_scale = s_scale + n_blk * BLOCK_N;
             const float* t_shift = s_shift + n_blk * BLOCK_N;
@@ -276,89 +292,116 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             mbar_wait(tfull(acc), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            float head_acc = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(t_row + (uint32_t)c0, r);
-                tmem_ld_wait();
-                float v[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaxf(fmaf(__uint_as_float(r[i]), t_scale[c0 + i], t_shift[c0 + i]), a.relu_floor);
+            float2 head_acc2 = make_float2(0.f, 0.f);                // even / odd channel partial sums of the 1x1 head
+            // one 32-column group of the accumulator row: affine (+ ReLU) -> bf16 -> staging / global (+ pool | head)
+            auto group = [&](const int c0, const bool first_half, const uint32_t (&r)[32]) {
+                const float4* sc4 = reinterpret_cast<const float4*>(t_scale + c0);
+                const float4* sh4 = reinterpret_cast<const float4*>(t_shift + c0);
                 if (a.epi == HEPI_HEAD) {
+                    const float4* hw4 = reinterpret_cast<const float4*>(s_head + c0);
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) head_acc = fmaf(v[i], s_head[c0 + i], head_acc);
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sc = sc4[i], sh = sh4[i], hw = hw4[i];
+                        float2 y0 = pk_fma(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                        float2 y1 = pk_fma(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                        y0.x = fmaxf(y0.x, a.relu_floor); y0.y = fmaxf(y0.y, a.relu_floor);
+                        y1.x = fmaxf(y1.x, a.relu_floor); y1.y = fmaxf(y1.y, a.relu_floor);
+                        head_acc2 = pk_fma(y0, make_float2(hw.x, hw.y), head_acc2);
+                        head_acc2 = pk_fma(y1, make_float2(hw.z, hw.w), head_acc2);
+                    }
+                    return;
+                }
+                // packed fp32x2 affine, ReLU folded into the bf16x2 conversion (relu_floor is 0 or -inf)
+                uint32_t pk[16];
+                if (a.relu_floor == 0.f) {                            // warp-uniform
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sc = sc4[i], sh = sh4[i];
+                        const float2 y0 = pk_fma(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                        const float2 y1 = pk_fma(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                        pk[2 * i] = pack_relu_bf16x2(y0.x, y0.y); pk[2 * i + 1] = pack_relu_bf16x2(y1.x, y1.y);
+                    }
                 } else {
-                    uint32_t pk[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                        pk[i] = *reinterpret_cast<uint32_t*>(&p);
-                    }
-                    const int n = n_blk * BLOCK_N + c0;
-                    const bool first_half = (c0 & 32) == 0;
-                    uint32_t o_stage = 0, p_stage = 0;
-                    if (a.tma_store) {                                // warp-uniform
-                        const uint32_t buf = store_groups & 1u;
-                        o_stage = smem_base + stage_off + buf * H_OUT_STAGE;
-                        p_stage = smem_base + stage_off + 2u * H_OUT_STAGE + buf * H_POOL_STAGE;
-                        if (first_half) {                             // this buffer's previous TMA store must have read it
-                            if (et == 0) bulk_wait_read<1>();
-                            named_bar_sync(1, H_EPI_THREADS);
-                        }
-                        const uint32_t rbase = o_stage + (uint32_t)row * 128u;
-                        const uint32_t cbase = first_half ? 0u : 4u;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            st_shared_v4(rbase + (((cbase + i) ^ ((uint32_t)row & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                    } else if (valid) {
-                        uint4* d4 = reinterpret_cast<uint4*>(a.out + (((long long)img * a.H + y) * a.W + x) * a.c_out + n);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                    }
-                    if (a.pool_out) {                                 // warp-uniform
-                        // values are post-ReLU (>= 0) and rows outside the image are never read by a writer (floor pooling),
-                        // so a plain max over the 2x2 lane window is exact
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            __nv_bfloat162 m0 = *reinterpret_cast<__nv_bfloat162*>(&pk[i]);
-                            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
-                            m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&o1));
-                            uint32_t mm = *reinterpret_cast<uint32_t*>(&m0);
-                            uint32_t o8 = __shfl_xor_sync(0xffffffffu, mm, 8);
-                            m0 = __hmax2(m0, *reinterpret_cast<__nv_bfloat162*>(&o8));
-                            pk[i] = *reinterpret_cast<uint32_t*>(&m0);
-                        }
-                        if (a.tma_store) {
-                            if (!(lx & 1) && !(ly & 1)) {
-                                const uint32_t pr = (uint32_t)((ly >> 1) * 4 + (lx >> 1));
-                                const uint32_t rbase = p_stage + pr * 128u;
-                                const uint32_t cbase = first_half ? 0u : 4u;
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    st_shared_v4(rbase + (((cbase + i) ^ (pr & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                            }
-                        } else if (pool_writer) {
-                            uint4* d4 = reinterpret_cast<uint4*>(a.pool_out + (((long long)img * Hp + (y >> 1)) * Wp + (x >> 1)) * a.c_out + n);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-                        }
-                    }
-                    if (a.tma_store && !first_half) {                 // a 64-channel group is staged: hand it to the TMA engine
-                        fence_proxy_async();
-                        named_bar_sync(1, H_EPI_THREADS);
-                        if (et == 0) {
-                            const int ch0 = n_blk * BLOCK_N + (c0 - 32);
-                            tma_store_4d(&tmOut, o_stage, ch0, tx * H_TW, ty * H_TH, img);
-                            if (a.pool_out) tma_store_4d(&tmPool, p_stage, ch0, tx * (H_TW / 2), ty * (H_TH / 2), img);
-                            bulk_commit();
-                        }
-                        ++store_groups;
+                    for (int i = 0; i < 8; ++i) {
+                        const float4 sc = sc4[i], sh = sh4[i];
+                        const float2 y0 = pk_fma(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                        const float2 y1 = pk_fma(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                        pk[2 * i] = pack_bf16x2(y0.x, y0.y); pk[2 * i + 1] = pack_bf16x2(y1.x, y1.y);
                     }
                 }
+                const int n = n_blk * BLOCK_N + c0;
+                const uint32_t cbase = first_half ? 0u : 4u;
+                uint32_t o_stage = 0, p_stage = 0;
+                if (a.tma_store) {                                    // warp-uniform
+                    const uint32_t buf = store_groups & 1u;
+                    o_stage = smem_base + stage_off + buf * H_OUT_STAGE;
+                    p_stage = smem_base + stage_off + 2u * H_OUT_STAGE + buf * H_POOL_STAGE;
+                    if (first_half) {                                 // this buffer's previous TMA store must have read it
+                        if (et == 0) bulk_wait_read<1>();
+                        named_bar_sync(1, H_EPI_THREADS);
+                    }
+                    const uint32_t rbase = o_stage + (uint32_t)row * 128u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        st_shared_v4(rbase + (((cbase + i) ^ ((uint32_t)row & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                } else if (valid) {
+                    uint4* d4 = reinterpret_cast<uint4*>(a.out + (((long long)img * a.H + y) * a.W + x) * a.c_out + n);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                }
+                if (a.pool_out) {                                     // warp-uniform
+                    // 2x2 max over the lane window {l, l^1, l^8, l^9} by halving exchanges: each lane sends the half of its
+                    // registers the partner keeps, so 12 shuffles (not 32) leave every lane with ONE 16-byte piece (8 channels)
+                    // of the pooled pixel: piece index = 2*(lx&1) + (ly&1).  Values are post-ReLU or plain maxima either way;
+                    // windows hanging over the image edge only feed pooled pixels that are clipped / not written (floor pooling).
+                    const bool ox = lx & 1, oy = ly & 1;
+                    uint32_t m1[8], m2[4];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t keep = ox ? pk[i + 8] : pk[i], send = ox ? pk[i] : pk[i + 8];
+                        m1[i] = bf16x2_max(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t keep = oy ? m1[i + 4] : m1[i], send = oy ? m1[i] : m1[i + 4];
+                        m2[i] = bf16x2_max(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+                    }
+                    const uint32_t piece = (ox ? 2u : 0u) + (oy ? 1u : 0u);
+                    if (a.tma_store) {
+                        const uint32_t pr = (uint32_t)((ly >> 1) * 4 + (lx >> 1));
+                        st_shared_v4(p_stage + pr * 128u + (((cbase + piece) ^ (pr & 7u)) << 4), m2[0], m2[1], m2[2], m2[3]);
+                    } else if (pool_px) {
+                        *reinterpret_cast<uint4*>(a.pool_out + (((long long)img * Hp + (y >> 1)) * Wp + (x >> 1)) * a.c_out + n + piece * 8) =
+                            make_uint4(m2[0], m2[1], m2[2], m2[3]);
+                    }
+                }
+                if (a.tma_store && !first_half) {                     // a 64-channel group is staged: hand it to the TMA engine
+                    fence_proxy_async();
+                    named_bar_sync(1, H_EPI_THREADS);
+                    if (et == 0) {
+                        const int ch0 = n_blk * BLOCK_N + (c0 - 32);
+                        tma_store_4d(&tmOut, o_stage, ch0, tx * H_TW, ty * H_TH, img);
+                        if (a.pool_out) tma_store_4d(&tmPool, p_stage, ch0, tx * (H_TW / 2), ty * (H_TH / 2), img);
+                        bulk_commit();
+                    }
+                    ++store_groups;
+                }
+            };
+            // the TMEM load of the next 32 columns is in flight while the current group is processed
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row, r0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
+                group(c0, true, r0);
+                tmem_ld_wait();
+                if (c0 + 64 < BLOCK_N) tmem_ld32(t_row + (uint32_t)(c0 + 64), r0);
+                group(c0 + 32, false, r1);
             }
             if (a.epi == HEPI_HEAD && valid)
-                a.head_out[((long long)img * a.H + y) * a.W + x] = head_acc + a.head_b[0];
+                a.head_out[((long long)img * a.H + y) * a.W + x] = (head_acc2.x + head_acc2.y) + a.head_b[0];
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {                                         // one arrival per epilogue warp (of both CTAs) frees the accumulator
@@ -459,6 +502,7 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     args.n_img = n; args.H = h; args.W = w;
     args.tiles_x = (w + H_TW - 1) / H_TW; args.tiles_y = (h + H_TH - 1) / H_TH;
     args.c_out = c_out; args.n_blocks = c_out / block_n;
+    args.div_nb = make_fastdiv(args.n_blocks); args.div_tpi = make_fastdiv(args.tiles_x * args.tiles_y); args.div_tx = make_fastdiv(args.tiles_x);
     const long long tiles = (long long)n * args.tiles_x * args.tiles_y * args.n_blocks;
     if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
     args.num_tiles = (int)tiles;
