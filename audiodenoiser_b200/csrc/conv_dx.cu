@@ -1,0 +1,369 @@
+// conv_dx.cu -- the 64-OUTPUT-CHANNEL 3x3 convs of the reference UNet (code/model.py:11-16 at full resolution: downconv1's
+// second conv, upconv4's two convs, the conv in front of the 1x1 head, model.py:68,93) as a tcgen05 implicit GEMM whose N
+// dimension carries the three HORIZONTAL taps:
+//
+//   D[(row r, halo column xh), (kx, co)] += A_ky[(r, xh), ci] * W[ky][(kx, co), ci]^T        ky = 0..2, ci in 64-channel chunks
+//   out[r, x, co] = D[(r, x), kx=0] + D[(r, x+1), kx=1] + D[(r, x+2), kx=2]                   (halo column xh = x + 1 + (kx-1))
+//
+// Why: with N = 64 a 128x64x16 UMMA reads 4 KB of A + 2 KB of B from shared memory for 32 clk of tensor time, and the
+// shared-memory operand path delivers ~96 B/clk (measured: those layers ran at 72 clk per UMMA, 0.5 of the tensor peak,
+// profiles/README.md).  Folding kx into N makes it 128x192x16: 4 KB + 6 KB for 98 clk of tensor time -- the A bytes per MAC drop
+// 3x and the three vertical taps are three whole-row offsets into one halo tile (1024-byte aligned descriptors).  The price: the
+// tile is 8 rows x 16 halo columns of which 14 are outputs (87.5 % useful rows), and the epilogue adds three accumulator
+// columns across neighbouring lanes (two shuffles per output value) -- the lanes of one image row sit in one half warp.
+//
+//   A operand   4-D TMA box {64 ch, 16 px, 10 rows, 1 image} per 64-channel chunk at (x0 - 1, y0 - 1): zero OOB fill = conv
+//               padding and the F.pad of the up-sampled half of a concat (model.py:44-49).  UMMA A for ky = plain K-major
+//               SWIZZLE_128B tile of 128 rows at base + ky * 2048 B.
+//   B operand   the packed weights [co][tap][ci] (adn_pack_conv3x3_weight_bf16) loaded ONCE per CTA as 9 * chunks boxes {64, 64}
+//               into [chunk][ky][kx][co] order: one (chunk, ky) operand = 192 consecutive rows.
+//   roles       warp 0 A producer, warp 1 UMMA issuer, warp 2 weight loader + TMEM allocator, warps 3..10 epilogue: two sets of
+//               four warps (one per TMEM lane quadrant), set s owning output channels [32 s, 32 s + 32)
+//               (tcgen05.ld -> neighbour-lane sum -> fp32 scale/shift -> ReLU -> bf16 -> the warp's own swizzled staging -> its own
+//               TMA store of a {32 ch, 14 px, 2 rows} box, + fused 2x2 max-pool {32, 7, 1} | fused 1x1 head): no CTA-wide
+//               barrier anywhere in the tile loop.  Two TMEM accumulators, released as soon
+//               as a warp holds its columns in registers.  With K = 576 these layers are epilogue-bound: one warp per
+//               scheduler could not hide the shuffle / TMEM latencies (measured 1.98 ms for downconv1's second conv with one
+//               set).
+#include "tc_common.cuh"
+
+namespace adn {
+
+constexpr int X_TW = 14, X_TH = 8;                  // output pixels of a tile
+constexpr int X_PITCH = 16, X_ROWS = X_TH + 2;      // halo tile: 10 rows x 16 pixels
+constexpr int X_A_STAGE = X_ROWS * X_PITCH * 128;   // 20 480 B
+constexpr int X_B_TAP = 64 * 128;                   // one (tap, chunk) weight box
+constexpr int X_B_BLOCK = 3 * X_B_TAP;              // one (chunk, ky) operand: 192 rows
+constexpr int X_OUT_STAGE = 2048;                   // per epilogue warp: 2 rows x 14 px x 32 ch bf16 = 1 792 B, SWIZZLE_64B
+constexpr int X_POOL_STAGE = 512;                   // per epilogue warp: 7 pooled px x 32 ch = 448 B
+constexpr int X_THREADS = 352, X_EPI_THREADS = 256;   // 3 role warps + two sets of 4 epilogue warps
+constexpr int X_MAX_A = 4;
+constexpr int X_AUX_F32 = 3 * 64 + 2 * 128;        // scale, shift, head weights, head partials
+constexpr int X_ACC_COLS = 256;                     // TMEM column pitch of the two accumulators (192 used)
+
+struct DxArgs {
+    int c0_chunks, c1_chunks;
+    int n_img, H, W;
+    int tiles_x, tiles_y, num_tiles;
+    FastDiv div_tpi, div_tx;
+    int head;                      // 1: fused 1x1 head (fp32 out), 0: NHWC bf16 out (+ optional pool)
+    int pool;
+    int a_stages;
+    float relu_floor;
+    const float* scale;
+    const float* shift;
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+};
+
+__global__ void __launch_bounds__(X_THREADS, 1)
+conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ CUtensorMap tmPool, const DxArgs a) {
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+    const int chunks = a.c0_chunks + a.c1_chunks;
+
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + (uint32_t)a.a_stages * X_A_STAGE;
+    const uint32_t stage_off = (uint32_t)a.a_stages * X_A_STAGE + (uint32_t)(chunks * 3) * X_B_BLOCK;
+    const uint32_t stage_bytes = a.head ? 0u : (8u * X_OUT_STAGE + (a.pool ? 8u * X_POOL_STAGE : 0u));
+    const uint32_t aux_off = stage_off + stage_bytes;
+    float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
+    float* s_shift = s_scale + 64;
+    float* s_head = s_shift + 64;
+    float* s_hpart = s_head + 64;                                     // [2][128] head partial sums of epilogue set 1
+    const uint32_t bar_base = smem_base + aux_off + X_AUX_F32 * 4;
+    auto full_a = [&](int s) { return bar_base + 8u * s; };
+    auto empty_a = [&](int s) { return bar_base + 8u * (X_MAX_A + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (2 * X_MAX_A + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (2 * X_MAX_A + 2 + s); };
+    const uint32_t bres = bar_base + 8u * (2 * X_MAX_A + 4);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + aux_off + X_AUX_F32 * 4 + (2 * X_MAX_A + 5) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmB);
+        if (!a.head) { tma_prefetch_desc(&tmOut); if (a.pool) tma_prefetch_desc(&tmPool); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < X_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), X_EPI_THREADS / 32); }
+        mbar_init(bres, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int tiles_per_img = a.tiles_x * a.tiles_y;
+
+    if (warp == 0) {
+        // ===================================================================== A producer: one halo tile per (tile, chunk)
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+                const int img = fast_div(t, a.div_tpi);
+                const int rem = t - img * tiles_per_img;
+                const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
+                for (int ch = 0; ch < chunks; ++ch) {
+                    mbar_wait(empty_a(stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(full_a(stage), X_A_STAGE);
+                    const CUtensorMap* map = (ch < a.c0_chunks) ? &tmA0 : &tmA1;
+                    const int c = (ch < a.c0_chunks ? ch : ch - a.c0_chunks) * 64;
+                    tma_load_4d(a_base + (uint32_t)stage * X_A_STAGE, map, full_a(stage), c, tx * X_TW - 1, ty * X_TH - 1, img);
+                    if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================================== weights: resident for the CTA's lifetime
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bres, (uint32_t)(9 * chunks) * X_B_TAP);
+            for (int ch = 0; ch < chunks; ++ch)
+                for (int tap = 0; tap < 9; ++tap)
+                    tma_load_2d(b_base + (uint32_t)(ch * 9 + tap) * X_B_TAP, &tmB, bres, (tap * chunks + ch) * 64, 0);
+        }
+    } else if (warp == 1) {
+        // ===================================================================== UMMA issuer (warp-uniform flow, one elected lane)
+        constexpr uint32_t idesc = make_idesc(192, 128);
+        int sa = 0; uint32_t pa = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        mbar_wait(bres, 0);
+        tc_fence_after();
+        const uint64_t db_base = make_sw128_desc(b_base);
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            mbar_wait(tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * X_ACC_COLS);
+            for (int ch = 0; ch < chunks; ++ch) {
+                mbar_wait(full_a(sa), pa);
+                tc_fence_after();
+                const uint64_t da = make_sw128_desc(a_base + (uint32_t)sa * X_A_STAGE);
+                const uint64_t db = db_base + (uint64_t)((uint32_t)(ch * 3) * (X_B_BLOCK >> 4));
+                if (elect_one()) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, da + (uint64_t)((ky * X_PITCH * 128 + k * 32) >> 4), db + (uint64_t)((ky * X_B_BLOCK + k * 32) >> 4),
+                                      idesc, (ky | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                    umma_commit(empty_a(sa));
+                }
+                __syncwarp();
+                if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
+            }
+            if (elect_one()) umma_commit(tfull(acc));
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else {
+        // ===================================================================== epilogue (warps 3..10; TMEM lane quadrant = warp & 3)
+        const int quad = warp & 3;
+        const int et = threadIdx.x - 96;                             // 0..255
+        const int set = (warp - 3) >> 2;                             // channel half owned by this warp
+        const int r = quad * 2 + (lane >> 4), xh = lane & 15;         // tile row, halo column of this lane's accumulator row
+        const bool out_lane = xh >= 1 && xh <= X_TW;
+        const int xo = xh - 1;
+        if (et < 64) { s_scale[et] = a.scale[et]; s_shift[et] = a.shift[et]; if (a.head) s_head[et] = a.head_w[et]; }
+        named_bar_sync(1, X_EPI_THREADS);
+        // 2x2 pool partners: (xo even, xo + 1) along x = lanes (xh odd, xh + 1); (r even, r + 1) along y = lanes l, l ^ 16
+        const bool x_first = xh & 1, y_first = !(lane & 16);
+        const int x_partner = x_first ? ((lane + 1) & 31) : ((lane + 31) & 31);
+        // every epilogue warp stages and stores its own {32 ch, 14 px, 2 rows} box (+ {32, 7, 1} pooled): no CTA-wide barrier
+        const int ew = warp - 3;                                      // 0..7
+        const uint32_t srow = (uint32_t)((lane >> 4) * X_TW + xo);    // staging row (64 B) of this lane's output pixel
+        const uint32_t prow = (uint32_t)(xo >> 1);
+        const uint32_t o_stage = smem_base + stage_off + (uint32_t)ew * X_OUT_STAGE;
+        const uint32_t p_stage = smem_base + stage_off + 8u * X_OUT_STAGE + (uint32_t)ew * X_POOL_STAGE;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t store_groups = 0;
+        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            const int img = fast_div(t, a.div_tpi);
+            const int rem = t - img * tiles_per_img;
+            const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
+            const int x = tx * X_TW + xo, y = ty * X_TH + r;
+            mbar_wait(tfull(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * X_ACC_COLS);
+            float2 head_acc2 = make_float2(0.f, 0.f);
+
+            // 16 output channels: sum the three kx column blocks across neighbouring lanes, affine (+ ReLU), pack, stage
+            auto group = [&](const int g, const uint32_t (&k0)[16], const uint32_t (&k1)[16], const uint32_t (&k2)[16]) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(k0[i]), 1);
+                    const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(k2[i]), 1);
+                    v[i] = (left + __uint_as_float(k1[i])) + right;
+                }
+                const float4* sc4 = reinterpret_cast<const float4*>(s_scale + g * 16);
+                const float4* sh4 = reinterpret_cast<const float4*>(s_shift + g * 16);
+                float2 y[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 sc = sc4[i], sh = sh4[i];
+                    y[2 * i] = pk_fma(make_float2(v[4 * i], v[4 * i + 1]), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                    y[2 * i + 1] = pk_fma(make_float2(v[4 * i + 2], v[4 * i + 3]), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                }
+                if (a.head) {                                         // warp-uniform
+                    const float4* hw4 = reinterpret_cast<const float4*>(s_head + g * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 hw = hw4[i];
+                        float2 y0 = y[2 * i], y1 = y[2 * i + 1];
+                        y0.x = fmaxf(y0.x, a.relu_floor); y0.y = fmaxf(y0.y, a.relu_floor);
+                        y1.x = fmaxf(y1.x, a.relu_floor); y1.y = fmaxf(y1.y, a.relu_floor);
+                        head_acc2 = pk_fma(y0, make_float2(hw.x, hw.y), head_acc2);
+                        head_acc2 = pk_fma(y1, make_float2(hw.z, hw.w), head_acc2);
+                    }
+                    return;
+                }
+                uint32_t pk[8];
+                if (a.relu_floor == 0.f) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_relu_bf16x2(y[i].x, y[i].y);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(y[i].x, y[i].y);
+                }
+                const uint32_t c0 = ((uint32_t)g & 1u) * 2u;             // 16-byte chunk of this group within the warp's 32 channels
+                if (out_lane) {
+                    const uint32_t rbase = o_stage + srow * 64u, sw = (srow >> 1) & 3u;
+                    st_shared_v4(rbase + ((c0 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                    st_shared_v4(rbase + (((c0 + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+                }
+                if (a.pool) {                                         // warp-uniform
+                    // halving exchanges: along x the first lane keeps registers 0..3, along y the first keeps 0..1; every lane
+                    // ends with ONE 8-byte piece (4 channels) of its 2x2 window's pooled pixel
+                    uint32_t m1[4], m2[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t keep = x_first ? pk[i] : pk[i + 4], send = x_first ? pk[i + 4] : pk[i];
+                        m1[i] = bf16x2_max(keep, __shfl_sync(0xffffffffu, send, x_partner));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const uint32_t keep = y_first ? m1[i] : m1[i + 2], send = y_first ? m1[i + 2] : m1[i];
+                        m2[i] = bf16x2_max(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+                    }
+                    if (out_lane) {
+                        const uint32_t c16 = c0 + (x_first ? 0u : 1u);
+                        st_shared_v2(p_stage + prow * 64u + ((c16 ^ ((prow >> 1) & 3u)) << 4) + (y_first ? 0u : 8u), m2[0], m2[1]);
+                    }
+                }
+            };
+
+            // this warp's 2 x 16 output channels x 3 kx blocks -> registers, then the accumulator is free for the MMA warp
+            uint32_t ra0[16], ra1[16], ra2[16], rb0[16], rb1[16], rb2[16];
+            const uint32_t t_set = t_row + (uint32_t)(set * 32);
+            tmem_ld16(t_set, ra0); tmem_ld16(t_set + 64u, ra1); tmem_ld16(t_set + 128u, ra2);
+            tmem_ld16(t_set + 16u, rb0); tmem_ld16(t_set + 80u, rb1); tmem_ld16(t_set + 144u, rb2);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            if (!a.head) {                                           // this warp's previous TMA store must have read its staging
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+            }
+            group(set * 2, ra0, ra1, ra2);
+            group(set * 2 + 1, rb0, rb1, rb2);
+
+            if (a.head) {                                            // set 1 hands its half of the dot product to set 0
+                float* part = s_hpart + (store_groups & 1u) * 128 + quad * 32 + lane;
+                if (set == 1) *part = head_acc2.x + head_acc2.y;
+                named_bar_sync(2 + quad, 64);                         // the two warps of this lane quadrant
+                if (set == 0 && out_lane && x < a.W && y < a.H)
+                    a.head_out[((long long)img * a.H + y) * a.W + x] = ((head_acc2.x + head_acc2.y) + *part) + a.head_b[0];
+                ++store_groups;
+            } else {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tmOut, o_stage, set * 32, tx * X_TW, ty * X_TH + quad * 2, img);
+                    if (a.pool) tma_store_4d(&tmPool, p_stage, set * 32, tx * (X_TW / 2), ty * (X_TH / 2) + quad, img);
+                    bulk_commit();
+                }
+            }
+        }
+        if (!a.head && lane == 0) bulk_wait<0>();                      // smem must outlive the last bulk stores
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+// (n,h,w,64) NHWC bf16 output written in per-warp boxes {32 ch, tw, th, 1}: 64-byte rows, SWIZZLE_64B
+static int make_store_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int tw, int th) {
+    PFN_tmapEncodeTiled enc = get_encode_fn();
+    if (!enc) return ADN_ERR_DRIVER;
+    cuuint64_t dims[4] = {64u, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    cuuint64_t strides[3] = {128u, (cuuint64_t)w * 128u, (cuuint64_t)h * w * 128u};
+    cuuint32_t box[4] = {32u, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
+}
+
+bool conv3x3_dx_eligible(int c0, int c1, int c_out) { return c_out == 64 && (c0 + c1) / 64 <= 2; }
+
+int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w, const void* w_packed,
+               const float* scale, const float* shift, float relu_floor, void* out, void* pool_out, const float* head_w,
+               const float* head_b, float* head_out, cudaStream_t stream) {
+    DxArgs args{};
+    args.c0_chunks = c0 / 64; args.c1_chunks = c1 / 64;
+    const int chunks = args.c0_chunks + args.c1_chunks;
+    args.n_img = n; args.H = h; args.W = w;
+    args.tiles_x = (w + X_TW - 1) / X_TW; args.tiles_y = (h + X_TH - 1) / X_TH;
+    const long long tiles = (long long)n * args.tiles_x * args.tiles_y;
+    if (tiles > 0x7fffffffLL) return ADN_ERR_ARG;
+    args.num_tiles = (int)tiles;
+    args.div_tpi = make_fastdiv(args.tiles_x * args.tiles_y); args.div_tx = make_fastdiv(args.tiles_x);
+    args.head = head_out ? 1 : 0;
+    args.pool = (!args.head && pool_out) ? 1 : 0;
+    args.relu_floor = relu_floor;
+    args.scale = scale; args.shift = shift;
+    args.head_w = head_w; args.head_b = head_b; args.head_out = head_out;
+
+    CUtensorMap mA0, mA1, mB, mOut, mPool;
+    int st = make_act_map(&mA0, src0, n, h, w, c0, X_PITCH, X_ROWS);
+    if (st != ADN_OK) return st;
+    if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, X_PITCH, X_ROWS); else mA1 = mA0;
+    if (st != ADN_OK) return st;
+    st = make_weight_map(&mB, w_packed, 64, 9 * (c0 + c1), 64);
+    if (st != ADN_OK) return st;
+    mOut = mA0; mPool = mA0;
+    if (!args.head) {
+        st = make_store_map(&mOut, out, n, h, w, X_TW, 2);
+        if (st != ADN_OK) return st;
+        if (args.pool) st = make_store_map(&mPool, pool_out, n, h / 2, w / 2, X_TW / 2, 1);
+        if (st != ADN_OK) return st;
+    }
+
+    constexpr int MAX_DYN = 232448;
+    const int AUX = X_AUX_F32 * 4 + (2 * X_MAX_A + 5) * 8 + 16;
+    const int fixed = 1024 + chunks * 3 * X_B_BLOCK + (args.head ? 0 : 8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0)) + AUX;
+    int stages = (MAX_DYN - fixed) / X_A_STAGE;
+    if (stages < 2) return ADN_ERR_ARG;
+    args.a_stages = stages > X_MAX_A ? X_MAX_A : stages;
+    const int smem = fixed + args.a_stages * X_A_STAGE;
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel, MAX_DYN, smem_set));
+    const int sms = num_sms();
+    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
+    conv3x3_dx_kernel<<<grid, X_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+}  // namespace adn

@@ -33,19 +33,6 @@ constexpr int H_POOL_STAGE = 32 * 128;             // its 2x2-pooled counterpart
 
 enum { HEPI_NHWC = 0, HEPI_HEAD = 2 };
 
-// x / d for 0 <= x < 2^31 as one multiply-high and a shift (d == 1: mul = 0 marks the identity).  The four runtime integer
-// divisions per tile cost ~180 dependent instructions in every role; in the epilogue warps that was a fifth of the tile.
-struct FastDiv { uint32_t mul, shr; };
-static FastDiv make_fastdiv(int d) {
-    FastDiv f{0u, 0u};
-    if (d <= 1) return f;
-    uint32_t k = 0; while ((1u << k) < (uint32_t)d) ++k;
-    const uint32_t p = 31 + k;
-    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
-    f.shr = p - 32;
-    return f;
-}
-__device__ __forceinline__ int fast_div(int x, FastDiv f) { return f.mul ? (int)(__umulhi((uint32_t)x, f.mul) >> f.shr) : x; }
 
 struct HaloArgs {
     int c0_chunks, c1_chunks;
@@ -419,6 +406,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static int g_dx_mode = 1;        // 0: never use the kx-in-N kernel of conv_dx.cu for the 64-output-channel layers
 static int g_pair_mode = 1;      // 0: never use CTA pairs; 1: where the layer is shared-memory-operand bound and a pair pays off
 
 template <int BLOCK_N, int NCTA>
@@ -496,6 +484,11 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     int st = check_device();
     if (st != ADN_OK) return st;
 
+    // 64 output channels over <= 128 input channels: the kx-in-N formulation (conv_dx.cu) reads a third of the A bytes per MAC
+    if (g_dx_mode && conv3x3_dx_eligible(c0, c1, c_out))
+        return conv3x3_dx(src0, c0, src1, c1, h1, w1, n, h, w, w_packed, scale, shift, relu ? 0.f : -INFINITY, out, pool_out,
+                          head_w, head_b, epi == HEPI_HEAD ? head_out : nullptr, stream);
+
     const int block_n = (c_out % 256 == 0) ? 256 : (c_out % 128 == 0) ? 128 : 64;
     HaloArgs args;
     args.c0_chunks = c0 / 64; args.c1_chunks = c1 / 64;
@@ -549,6 +542,7 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
 
 // tuning / debugging hook (not in the public header): 0 disables the CTA-pair kernels
 extern "C" void adn__conv_pair_mode(int mode) { adn::g_pair_mode = mode; }
+extern "C" void adn__conv_dx_mode(int mode) { adn::g_dx_mode = mode; }
 
 extern "C" int adn_conv3x3_bn_relu_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
                                         const void* w_packed, int c_out, const float* scale, const float* shift, void* out,

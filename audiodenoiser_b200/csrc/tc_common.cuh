@@ -7,6 +7,20 @@
 
 namespace adn {
 
+// x / d for 0 <= x < 2^31 as one multiply-high and a shift (d == 1: mul = 0 marks the identity).  The four runtime integer
+// divisions per tile cost ~180 dependent instructions in every role; in the epilogue warps that was a fifth of the tile.
+struct FastDiv { uint32_t mul, shr; };
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1) return f;
+    uint32_t k = 0; while ((1u << k) < (uint32_t)d) ++k;
+    const uint32_t p = 31 + k;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = p - 32;
+    return f;
+}
+__device__ __forceinline__ int fast_div(int x, FastDiv f) { return f.mul ? (int)(__umulhi((uint32_t)x, f.mul) >> f.shr) : x; }
+
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -77,6 +91,9 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
     asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
     return d;
 }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -117,6 +134,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -250,6 +275,12 @@ inline int make_weight_map(CUtensorMap* map, const void* ptr, int n_total, int k
     return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
 }
 
+
+// conv_dx.cu: 3x3 conv with 64 output channels, the three horizontal taps folded into the UMMA N dimension
+bool conv3x3_dx_eligible(int c0, int c1, int c_out);
+int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w, const void* w_packed,
+               const float* scale, const float* shift, float relu_floor, void* out, void* pool_out, const float* head_w,
+               const float* head_b, float* head_out, cudaStream_t stream);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
