@@ -37,7 +37,7 @@ constexpr int X_B_BLOCK = 3 * X_B_TAP;              // one (chunk, ky) operand: 
 constexpr int X_OUT_STAGE = 2048;                   // per epilogue warp: 2 rows x 14 px x 32 ch bf16 = 1 792 B, SWIZZLE_64B
 constexpr int X_POOL_STAGE = 512;                   // per epilogue warp: 7 pooled px x 32 ch = 448 B
 constexpr int X_THREADS = 352, X_EPI_THREADS = 256;   // 3 role warps + two sets of 4 epilogue warps
-constexpr int X_MAX_A = 4;
+constexpr int X_MAX_A = 6;
 constexpr int X_AUX_F32 = 3 * 64 + 2 * 128;        // scale, shift, head weights, head partials
 constexpr int X_ACC_COLS = 256;                     // TMEM column pitch of the two accumulators (192 used)
 
@@ -57,10 +57,21 @@ struct DxArgs {
     float* head_out;
 };
 
+// NCTA == 2: a CTA pair (cluster of 2, cta_group::2) computes TWO tiles with ONE 256x192x16 UMMA per k-step; each CTA holds its own
+// halo tile and the weight rows of HALF the output channels (columns [96 r, 96 r + 96) = [kx][32 channels] of CTA r), so a CTA
+// reads 4 KB of A + 3 KB of B per UMMA instead of 4 + 6: the single-CTA kernel runs at the shared-memory operand bandwidth
+// (tensor pipe 75 % active).  Barrier protocol as in conv_halo.cu: full / accumulator-empty barriers live in the leader, a peer's
+// TMA completes its bytes there, commits are multicast to both CTAs.
+template <int NCTA>
 __global__ void __launch_bounds__(X_THREADS, 1)
 conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                   const __grid_constant__ CUtensorMap tmPool, const DxArgs a) {
+    constexpr bool PAIR = (NCTA == 2);
+    constexpr int B_TAP = X_B_TAP / NCTA;                            // this CTA's rows of one (tap, chunk) weight box
+    constexpr int B_BLOCK = 3 * B_TAP;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = (cta_rank == 0);
     extern __shared__ uint8_t smem_dyn[];
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
@@ -68,7 +79,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)a.a_stages * X_A_STAGE;
-    const uint32_t stage_off = (uint32_t)a.a_stages * X_A_STAGE + (uint32_t)(chunks * 3) * X_B_BLOCK;
+    const uint32_t stage_off = (uint32_t)a.a_stages * X_A_STAGE + (uint32_t)(chunks * 3) * B_BLOCK;
     const uint32_t stage_bytes = a.head ? 0u : (8u * X_OUT_STAGE + (a.pool ? 8u * X_POOL_STAGE : 0u));
     const uint32_t aux_off = stage_off + stage_bytes;
     float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
@@ -90,31 +101,44 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < X_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), X_EPI_THREADS / 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), NCTA * X_EPI_THREADS / 32); }
         mbar_init(bres, 1);
         fence_barrier_init();
     }
-    if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+    if (warp == 2) {
+        if (PAIR) { tmem_alloc_pair(smem_u32(tmem_ptr_smem), 512); tmem_relinquish_pair(); }
+        else { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();           // peers must see initialised barriers before any remote arrive
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_smem;
+    const uint32_t tmem_own = *tmem_ptr_smem;
+    const uint32_t tmem_base = PAIR ? ld_shared_cluster_u32(mapa_shared(smem_u32(tmem_ptr_smem), 0)) : tmem_own;
     const int tiles_per_img = a.tiles_x * a.tiles_y;
+    // work items: single CTA -> tile; pair -> two consecutive tiles, this CTA taking 2 w + rank (the odd tail is an all-zero
+    // tile of image n_img whose stores are clipped away)
+    const int work_total = PAIR ? (a.num_tiles + 1) / 2 : a.num_tiles;
+    const int work_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int work_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto tile_of = [&](int w) { return PAIR ? 2 * w + (int)cta_rank : w; };
 
     if (warp == 0) {
         // ===================================================================== A producer: one halo tile per (tile, chunk)
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+            for (int w = work_first; w < work_total; w += work_step) {
+                const int t = tile_of(w);
                 const int img = fast_div(t, a.div_tpi);
                 const int rem = t - img * tiles_per_img;
                 const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
                 for (int ch = 0; ch < chunks; ++ch) {
                     mbar_wait(empty_a(stage), phase ^ 1u);
-                    mbar_arrive_expect_tx(full_a(stage), X_A_STAGE);
+                    if (leader) mbar_arrive_expect_tx(full_a(stage), NCTA * X_A_STAGE);
                     const CUtensorMap* map = (ch < a.c0_chunks) ? &tmA0 : &tmA1;
                     const int c = (ch < a.c0_chunks ? ch : ch - a.c0_chunks) * 64;
-                    tma_load_4d(a_base + (uint32_t)stage * X_A_STAGE, map, full_a(stage), c, tx * X_TW - 1, ty * X_TH - 1, img);
+                    const uint32_t dst = a_base + (uint32_t)stage * X_A_STAGE;
+                    if (PAIR) tma_load_4d_pair(dst, map, mapa_shared(full_a(stage), 0), c, tx * X_TW - 1, ty * X_TH - 1, img);
+                    else tma_load_4d(dst, map, full_a(stage), c, tx * X_TW - 1, ty * X_TH - 1, img);
                     if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -122,20 +146,31 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     } else if (warp == 2) {
         // ===================================================================== weights: resident for the CTA's lifetime
         if (lane == 0) {
-            mbar_arrive_expect_tx(bres, (uint32_t)(9 * chunks) * X_B_TAP);
+            if (leader) mbar_arrive_expect_tx(bres, (uint32_t)(NCTA * 9 * chunks) * B_TAP);
+            const uint32_t sig = PAIR ? mapa_shared(bres, 0) : bres;
+            const int row0 = (int)cta_rank * (64 / NCTA);            // this CTA's output channels
             for (int ch = 0; ch < chunks; ++ch)
-                for (int tap = 0; tap < 9; ++tap)
-                    tma_load_2d(b_base + (uint32_t)(ch * 9 + tap) * X_B_TAP, &tmB, bres, (tap * chunks + ch) * 64, 0);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t dst = b_base + (uint32_t)(ch * 9 + tap) * B_TAP;
+                    if (PAIR) tma_load_2d_pair(dst, &tmB, sig, (tap * chunks + ch) * 64, row0);
+                    else tma_load_2d(dst, &tmB, sig, (tap * chunks + ch) * 64, row0);
+                }
         }
     } else if (warp == 1) {
-        // ===================================================================== UMMA issuer (warp-uniform flow, one elected lane)
-        constexpr uint32_t idesc = make_idesc(192, 128);
+      // ===================================================================== UMMA issuer (warp-uniform flow, one elected lane;
+      // in a pair only the leader's warp issues, for both CTAs)
+      if (leader) {
+        constexpr uint32_t idesc = make_idesc(192, 128 * NCTA);
+        auto umma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accf) {
+            if (PAIR) umma_bf16_pair(d, da, db, idesc, accf); else umma_bf16(d, da, db, idesc, accf);
+        };
+        auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
         int sa = 0; uint32_t pa = 0;
         int acc = 0; uint32_t acc_phase = 0;
         mbar_wait(bres, 0);
         tc_fence_after();
         const uint64_t db_base = make_sw128_desc(b_base);
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        for (int w = work_first; w < work_total; w += work_step) {
             mbar_wait(tempty(acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * X_ACC_COLS);
@@ -143,23 +178,24 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 mbar_wait(full_a(sa), pa);
                 tc_fence_after();
                 const uint64_t da = make_sw128_desc(a_base + (uint32_t)sa * X_A_STAGE);
-                const uint64_t db = db_base + (uint64_t)((uint32_t)(ch * 3) * (X_B_BLOCK >> 4));
+                const uint64_t db = db_base + (uint64_t)((uint32_t)(ch * 3) * (B_BLOCK >> 4));
                 if (elect_one()) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(d_tmem, da + (uint64_t)((ky * X_PITCH * 128 + k * 32) >> 4), db + (uint64_t)((ky * X_B_BLOCK + k * 32) >> 4),
-                                      idesc, (ky | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
-                    umma_commit(empty_a(sa));
+                            umma(d_tmem, da + (uint64_t)((ky * X_PITCH * 128 + k * 32) >> 4), db + (uint64_t)((ky * B_BLOCK + k * 32) >> 4),
+                                 (ky | k) != 0 ? 1u : (ch != 0 ? 1u : 0u));
+                    commit(empty_a(sa));
                 }
                 __syncwarp();
                 if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
             }
-            if (elect_one()) umma_commit(tfull(acc));
+            if (elect_one()) commit(tfull(acc));
             __syncwarp();
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
+      }
     } else {
         // ===================================================================== epilogue (warps 3..10; TMEM lane quadrant = warp & 3)
         const int quad = warp & 3;
@@ -181,8 +217,13 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t p_stage = smem_base + stage_off + 8u * X_OUT_STAGE + (uint32_t)ew * X_POOL_STAGE;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
-        for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-            const int img = fast_div(t, a.div_tpi);
+        const uint32_t tempty_sig0 = PAIR ? mapa_shared(tempty(0), 0) : tempty(0);
+        const uint32_t tempty_sig1 = PAIR ? mapa_shared(tempty(1), 0) : tempty(1);
+        // accumulator columns of (kx, 16-channel group gl of this warp's channel half)
+        auto acc_col = [&](int kx, int gl) { return (uint32_t)(PAIR ? set * 96 + kx * 32 + gl * 16 : kx * 64 + set * 32 + gl * 16); };
+        for (int w = work_first; w < work_total; w += work_step) {
+            const int t = tile_of(w);
+            const int img = fast_div(t, a.div_tpi);                 // == n_img for the padding tile of an odd pair
             const int rem = t - img * tiles_per_img;
             const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
             const int x = tx * X_TW + xo, y = ty * X_TH + r;
@@ -259,13 +300,14 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
             // this warp's 2 x 16 output channels x 3 kx blocks -> registers, then the accumulator is free for the MMA warp
             uint32_t ra0[16], ra1[16], ra2[16], rb0[16], rb1[16], rb2[16];
-            const uint32_t t_set = t_row + (uint32_t)(set * 32);
-            tmem_ld16(t_set, ra0); tmem_ld16(t_set + 64u, ra1); tmem_ld16(t_set + 128u, ra2);
-            tmem_ld16(t_set + 16u, rb0); tmem_ld16(t_set + 80u, rb1); tmem_ld16(t_set + 144u, rb2);
+            tmem_ld16(t_row + acc_col(0, 0), ra0); tmem_ld16(t_row + acc_col(1, 0), ra1); tmem_ld16(t_row + acc_col(2, 0), ra2);
+            tmem_ld16(t_row + acc_col(0, 1), rb0); tmem_ld16(t_row + acc_col(1, 1), rb1); tmem_ld16(t_row + acc_col(2, 1), rb2);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty(acc));
+            if (lane == 0) {                                         // one arrival per epilogue warp (of both CTAs) frees the accumulator
+                if (PAIR) mbar_arrive_cluster(acc ? tempty_sig1 : tempty_sig0); else mbar_arrive(tempty(acc));
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             if (!a.head) {                                           // this warp's previous TMA store must have read its staging
                 if (lane == 0) bulk_wait_read<0>();
@@ -278,7 +320,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 float* part = s_hpart + (store_groups & 1u) * 128 + quad * 32 + lane;
                 if (set == 1) *part = head_acc2.x + head_acc2.y;
                 named_bar_sync(2 + quad, 64);                         // the two warps of this lane quadrant
-                if (set == 0 && out_lane && x < a.W && y < a.H)
+                if (set == 0 && out_lane && x < a.W && y < a.H && t < a.num_tiles)
                     a.head_out[((long long)img * a.H + y) * a.W + x] = ((head_acc2.x + head_acc2.y) + *part) + a.head_b[0];
                 ++store_groups;
             } else {
@@ -295,9 +337,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();           // the peer may still read this CTA's smem / write its TMEM
     tc_fence_after();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == 2) { if (PAIR) tmem_dealloc_pair(tmem_own, 512); else tmem_dealloc(tmem_own, 512); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -314,6 +356,12 @@ static int make_store_map(CUtensorMap* map, const void* ptr, int n, int h, int w
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
 }
+
+// CTA pairs are OFF by default: measured on B200 (scripts/ab_conv_modes.py, batch 64) the 256x192x16 pair UMMA (96 weight rows per
+// CTA) runs 2.7x slower per instruction than the single-CTA 128x192x16 one -- upconv4.0 2.03 -> 2.59 ms, the K = 576 layers 2x
+// slower -- the same effect conv_halo.cu saw with 32 rows per CTA; only 64-row halves (N = 128 pairs) are fast.  Kept behind the
+// debug hook adn__conv_dx_mode(2) because the parity tests cover it.
+int g_dx_pair = 0;
 
 bool conv3x3_dx_eligible(int c0, int c1, int c_out) { return c_out == 64 && (c0 + c1) / 64 <= 2; }
 
@@ -340,8 +388,6 @@ int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w
     if (st != ADN_OK) return st;
     if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, X_PITCH, X_ROWS); else mA1 = mA0;
     if (st != ADN_OK) return st;
-    st = make_weight_map(&mB, w_packed, 64, 9 * (c0 + c1), 64);
-    if (st != ADN_OK) return st;
     mOut = mA0; mPool = mA0;
     if (!args.head) {
         st = make_store_map(&mOut, out, n, h, w, X_TW, 2);
@@ -352,16 +398,35 @@ int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w
 
     constexpr int MAX_DYN = 232448;
     const int AUX = X_AUX_F32 * 4 + (2 * X_MAX_A + 5) * 8 + 16;
-    const int fixed = 1024 + chunks * 3 * X_B_BLOCK + (args.head ? 0 : 8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0)) + AUX;
+    const int sms = num_sms();
+    const bool pair = g_dx_pair && args.num_tiles >= 2 * sms;
+    const int ncta = pair ? 2 : 1;
+    const int fixed = 1024 + chunks * 3 * (X_B_BLOCK / ncta) + (args.head ? 0 : 8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0)) + AUX;
     int stages = (MAX_DYN - fixed) / X_A_STAGE;
     if (stages < 2) return ADN_ERR_ARG;
     args.a_stages = stages > X_MAX_A ? X_MAX_A : stages;
     const int smem = fixed + args.a_stages * X_A_STAGE;
-    static unsigned char smem_set[64] = {0};
-    ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel, MAX_DYN, smem_set));
-    const int sms = num_sms();
-    const int grid = args.num_tiles < sms ? args.num_tiles : sms;
-    conv3x3_dx_kernel<<<grid, X_THREADS, smem, stream>>>(mA0, mA1, mB, mOut, mPool, args);
+    st = make_weight_map(&mB, w_packed, 64, 9 * (c0 + c1), 64 / ncta);
+    if (st != ADN_OK) return st;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    cfg.blockDim = dim3(X_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+    if (pair) {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<2>, MAX_DYN, smem_set));
+        const int pairs = (args.num_tiles + 1) / 2;
+        cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<2>, mA0, mA1, mB, mOut, mPool, args));
+    } else {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<1>, MAX_DYN, smem_set));
+        cfg.gridDim = dim3(args.num_tiles < sms ? args.num_tiles : sms);
+        cfg.attrs = nullptr; cfg.numAttrs = 0;
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<1>, mA0, mA1, mB, mOut, mPool, args));
+    }
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

@@ -19,10 +19,11 @@ lib.adn__conv_dx_mode.restype = None
 net = UNet().eval()
 net.load_state_dict(seeded_state_dict(3))
 x = torch.rand(batch, 1, 257, 1034, device="cuda")
-res = {0: {}, 1: {}}
+MODES = (0, 1, 2)
+res = {m: {} for m in MODES}
 with torch.no_grad():
     for rep in range(6):
-        for mode in (0, 1):
+        for mode in MODES:
             lib.adn__conv_dx_mode(mode)
             net.profile = []
             net(x)
@@ -32,11 +33,13 @@ with torch.no_grad():
                     d = res[mode].setdefault(layer, [0.0, 0, flops])
                     d[0] += a.elapsed_time(b); d[1] += 1
             net.profile = None
-tot = {0: 0.0, 1: 0.0}
+tot = {m: 0.0 for m in MODES}
+names = {0: "halo", 1: "dx", 2: "dx-pair"}
 for layer in res[0]:
-    m0 = res[0][layer][0] / res[0][layer][1]; m1 = res[1][layer][0] / res[1][layer][1]
-    tot[0] += m0; tot[1] += m1
+    ms = {m: res[m][layer][0] / res[m][layer][1] for m in MODES}
+    for m in MODES:
+        tot[m] += ms[m]
     fl = res[0][layer][2]
-    if abs(m0 - m1) / m0 > 0.03:
-        print(f"{layer:16s} halo {m0:7.3f} ms ({fl / m0 / 1e9:6.0f} TF)   dx {m1:7.3f} ms ({fl / m1 / 1e9:6.0f} TF)")
-print(f"forward total: halo {tot[0]:.3f} ms, dx {tot[1]:.3f} ms")
+    if max(ms.values()) / min(ms.values()) > 1.03:
+        print(f"{layer:16s} " + "   ".join(f"{names[m]} {ms[m]:7.3f} ms ({fl / ms[m] / 1e9:5.0f} TF)" for m in MODES))
+print("forward total: " + ", ".join(f"{names[m]} {tot[m]:.3f} ms" for m in MODES))
