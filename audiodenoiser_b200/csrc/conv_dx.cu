@@ -49,6 +49,7 @@ struct DxArgs {
     int head;                      // 1: fused 1x1 head (fp32 out), 0: NHWC bf16 out (+ optional pool)
     int pool;
     int a_stages;
+    int stage_bufs;                // 1 or 2 staging buffers per epilogue warp (2 when the weights leave room: one input chunk)
     float relu_floor;
     const float* scale;
     const float* shift;
@@ -80,7 +81,7 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)a.a_stages * X_A_STAGE;
     const uint32_t stage_off = (uint32_t)a.a_stages * X_A_STAGE + (uint32_t)(chunks * 3) * B_BLOCK;
-    const uint32_t stage_bytes = a.head ? 0u : (8u * X_OUT_STAGE + (a.pool ? 8u * X_POOL_STAGE : 0u));
+    const uint32_t stage_bytes = a.head ? 0u : (uint32_t)a.stage_bufs * (8u * X_OUT_STAGE + (a.pool ? 8u * X_POOL_STAGE : 0u));
     const uint32_t aux_off = stage_off + stage_bytes;
     float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
     float* s_shift = s_scale + 64;
@@ -213,8 +214,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int ew = warp - 3;                                      // 0..7
         const uint32_t srow = (uint32_t)((lane >> 4) * X_TW + xo);    // staging row (64 B) of this lane's output pixel
         const uint32_t prow = (uint32_t)(xo >> 1);
-        const uint32_t o_stage = smem_base + stage_off + (uint32_t)ew * X_OUT_STAGE;
-        const uint32_t p_stage = smem_base + stage_off + 8u * X_OUT_STAGE + (uint32_t)ew * X_POOL_STAGE;
+        const uint32_t o_stage0 = smem_base + stage_off + (uint32_t)(ew * a.stage_bufs) * X_OUT_STAGE;
+        const uint32_t p_stage0 = smem_base + stage_off + (uint32_t)(8 * a.stage_bufs) * X_OUT_STAGE + (uint32_t)(ew * a.stage_bufs) * X_POOL_STAGE;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
         const uint32_t tempty_sig0 = PAIR ? mapa_shared(tempty(0), 0) : tempty(0);
@@ -227,6 +228,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             const int rem = t - img * tiles_per_img;
             const int ty = fast_div(rem, a.div_tx), tx = rem - ty * a.tiles_x;
             const int x = tx * X_TW + xo, y = ty * X_TH + r;
+            const uint32_t buf = (a.stage_bufs == 2) ? (store_groups & 1u) : 0u;
+            const uint32_t o_stage = o_stage0 + buf * X_OUT_STAGE, p_stage = p_stage0 + buf * X_POOL_STAGE;
             mbar_wait(tfull(acc), acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * X_ACC_COLS);
@@ -309,8 +312,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 if (PAIR) mbar_arrive_cluster(acc ? tempty_sig1 : tempty_sig0); else mbar_arrive(tempty(acc));
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-            if (!a.head) {                                           // this warp's previous TMA store must have read its staging
-                if (lane == 0) bulk_wait_read<0>();
+            if (!a.head) {                                           // the TMA store that last used this staging buffer must have read it
+                if (elect_one()) { if (a.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
                 __syncwarp();
             }
             group(set * 2, ra0, ra1, ra2);
@@ -326,14 +329,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             } else {
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {                                   // the same lane every time (bulk groups are per thread); uniform
                     tma_store_4d(&tmOut, o_stage, set * 32, tx * X_TW, ty * X_TH + quad * 2, img);
                     if (a.pool) tma_store_4d(&tmPool, p_stage, set * 32, tx * (X_TW / 2), ty * (X_TH / 2) + quad, img);
                     bulk_commit();
                 }
+                ++store_groups;
             }
         }
-        if (!a.head && lane == 0) bulk_wait<0>();                      // smem must outlive the last bulk stores
+        __syncwarp();
+        if (!a.head && elect_one()) bulk_wait<0>();                      // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
@@ -401,7 +406,9 @@ int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w
     const int sms = num_sms();
     const bool pair = g_dx_pair && args.num_tiles >= 2 * sms;
     const int ncta = pair ? 2 : 1;
-    const int fixed = 1024 + chunks * 3 * (X_B_BLOCK / ncta) + (args.head ? 0 : 8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0)) + AUX;
+    args.stage_bufs = (chunks == 1) ? 2 : 1;
+    const int fixed = 1024 + chunks * 3 * (X_B_BLOCK / ncta) +
+                      (args.head ? 0 : args.stage_bufs * (8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0))) + AUX;
     int stages = (MAX_DYN - fixed) / X_A_STAGE;
     if (stages < 2) return ADN_ERR_ARG;
     args.a_stages = stages > X_MAX_A ? X_MAX_A : stages;

@@ -349,7 +349,7 @@ def run_b200(args):
                     tc[k] += agg[kind][k]
         tc_tflops = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
         peak_tc = peaks["bf16_sustained"]
-        roofline = {"kernel": "conv3x3_halo_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU, 17 launches/step incl. the head-fused one)", "bound": "tensor",
+        roofline = {"kernel": "conv3x3_halo_kernel + conv3x3_dx_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU: 14 + 3 launches/step, the 64-output-channel layers incl. the head-fused one run the kx-in-N variant)", "bound": "tensor",
                     "achieved": tc_tflops, "peak": peak_tc, "unit": "TFLOP/s", "frac": tc_tflops / peak_tc,
                     "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                     "launches_per_step": tc["launches"] // reps, "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),

@@ -107,6 +107,51 @@ def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
         assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))         # pooling of the stored values is exact
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("n,c0,c1,h,w,relu", [(3, 64, 0, 257, 188, 1), (2, 64, 64, 61, 90, 0), (5, 128, 0, 64, 256, 1)])
+def test_conv3x3_64_output_channels_all_kernels(mode, n, c0, c1, h, w, relu):
+    """The 64-output-channel layers have three implementations behind one entry point (debug hook adn__conv_dx_mode): the
+    halo-tile kernel (0), the kx-in-N kernel (1, default) and its CTA-pair variant (2).  All three must agree with F.conv2d,
+    with and without the activation, with the fused pool and across a concat."""
+    import ctypes
+    lib = _lib.load(); s = _lib.stream_ptr()
+    lib.adn__conv_dx_mode.argtypes = [ctypes.c_int]; lib.adn__conv_dx_mode.restype = None
+    g = torch.Generator().manual_seed(77 * h + w)
+    ci = c0 + c1
+    h1, w1 = (h - (h % 2), w - (w % 2)) if c1 else (0, 0)
+    x0 = bf16_round(torch.randn(n, c0, h, w, generator=g))
+    x1 = bf16_round(torch.randn(n, c1, h1, w1, generator=g)) if c1 else None
+    wt = bf16_round(torch.randn(64, ci, 3, 3, generator=g) * (2.0 / (9 * ci)) ** 0.5)
+    scale = 0.5 + torch.rand(64, generator=g); shift = 0.1 * torch.randn(64, generator=g)
+    xin = x0 if x1 is None else torch.cat([x0, F.pad(x1, [0, w - w1, 0, h - h1])], 1)
+    ref = F.conv2d(xin, wt, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    wp = torch.empty((64, 9, ci), dtype=torch.bfloat16, device=dev())
+    wd = wt.to(dev()).contiguous()
+    _lib.check(lib.adn_pack_conv3x3_weight_bf16(wd.data_ptr(), 64, ci, wp.data_ptr(), s))
+    a0 = to_nhwc_bf16(x0).to(dev()); a1 = to_nhwc_bf16(x1).to(dev()) if c1 else None
+    out = torch.zeros((n, h, w, 64), dtype=torch.bfloat16, device=dev())
+    pool = torch.zeros((n, h // 2, w // 2, 64), dtype=torch.bfloat16, device=dev())
+    sc, sh = scale.to(dev()), shift.to(dev())
+    try:
+        lib.adn__conv_dx_mode(mode)
+        if relu:
+            _lib.check(lib.adn_conv3x3_bn_relu_bf16(a0.data_ptr(), c0, a1.data_ptr() if c1 else 0, c1, h1, w1, n, h, w, wp.data_ptr(), 64,
+                                                    sc.data_ptr(), sh.data_ptr(), out.data_ptr(), pool.data_ptr(), s))
+        else:
+            _lib.check(lib.adn_conv3x3_affine_bf16(a0.data_ptr(), c0, a1.data_ptr() if c1 else 0, c1, h1, w1, n, h, w, wp.data_ptr(), 64,
+                                                   sc.data_ptr(), sh.data_ptr(), 0, out.data_ptr(), s))
+        torch.cuda.synchronize()
+    finally:
+        lib.adn__conv_dx_mode(1)
+    got = from_nhwc(out.cpu())
+    assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+    assert nrel(got, ref) <= 2.5e-3
+    if relu:
+        assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))
+
+
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
 def test_convt2x2(n, ci, co, h, w):
     lib = _lib.load(); s = _lib.stream_ptr()
