@@ -7,7 +7,7 @@ CMD="python bench.py --steps 2 --warmup 3 --variant R --no-cpu-baseline --train-
 $CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit $?"
-ncu --set full --clock-control none --import-source on -k regex:conv3x3_(halo|dx) -s 48 -c 17 -o gpurun_out/prof_conv -f $CMD > gpurun_out/ncu_conv.log 2>&1
+ncu --set full --clock-control none --import-source on -k "regex:conv3x3_(halo|dx)" -s 48 -c 17 -o gpurun_out/prof_conv -f $CMD > gpurun_out/ncu_conv.log 2>&1
 echo "conv full exit $?"
 python scripts/prof_train.py > gpurun_out/prof_train_plain.log 2>&1 || { echo "train plain failed"; exit 1; }
 ncu --set full --clock-control none --import-source on -k regex:wgrad_kernel -s 50 -c 25 -o gpurun_out/prof_wgrad -f python scripts/prof_train.py > gpurun_out/ncu_wgrad.log 2>&1
