@@ -34,11 +34,13 @@ constexpr int X_PITCH = 16, X_ROWS = X_TH + 2;      // halo tile: 10 rows x 16 p
 constexpr int X_A_STAGE = X_ROWS * X_PITCH * 128;   // 20 480 B
 constexpr int X_B_TAP = 64 * 128;                   // one (tap, chunk) weight box
 constexpr int X_B_BLOCK = 3 * X_B_TAP;              // one (chunk, ky) operand: 192 rows
-constexpr int X_OUT_STAGE = 2048;                   // per epilogue warp: 2 rows x 14 px x 32 ch bf16 = 1 792 B, SWIZZLE_64B
-constexpr int X_POOL_STAGE = 512;                   // per epilogue warp: 7 pooled px x 32 ch = 448 B
-constexpr int X_THREADS = 352, X_EPI_THREADS = 256;   // 3 role warps + two sets of 4 epilogue warps
+// per epilogue warp (SETS sets of 4 warps, each warp owning 64 / SETS channels of its 2 tile rows): staging of 2 rows x 14 px and
+// of 7 pooled px, rows of 64 B (SWIZZLE_64B) or 32 B (SWIZZLE_32B), padded to the swizzle period
+constexpr int x_out_stage(int sets) { return 2048 * 2 / sets; }
+constexpr int x_pool_stage(int sets) { return 512 * 2 / sets; }
+constexpr int x_threads(int sets) { return 96 + 128 * sets; }     // 3 role warps + SETS x 4 epilogue warps
 constexpr int X_MAX_A = 6;
-constexpr int X_AUX_F32 = 3 * 64 + 2 * 128;        // scale, shift, head weights, head partials
+constexpr int X_AUX_F32 = 3 * 64 + 2 * 3 * 128;    // scale, shift, head weights, head partials [2][SETS - 1][128]
 constexpr int X_ACC_COLS = 256;                     // TMEM column pitch of the two accumulators (192 used)
 
 struct DxArgs {
@@ -63,12 +65,15 @@ struct DxArgs {
 // reads 4 KB of A + 3 KB of B per UMMA instead of 4 + 6: the single-CTA kernel runs at the shared-memory operand bandwidth
 // (tensor pipe 75 % active).  Barrier protocol as in conv_halo.cu: full / accumulator-empty barriers live in the leader, a peer's
 // TMA completes its bytes there, commits are multicast to both CTAs.
-template <int NCTA>
-__global__ void __launch_bounds__(X_THREADS, 1)
+template <int NCTA, int SETS>
+__global__ void __launch_bounds__(x_threads(SETS), 1)
 conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                   const __grid_constant__ CUtensorMap tmPool, const DxArgs a) {
     constexpr bool PAIR = (NCTA == 2);
+    constexpr int X_EPI_THREADS = 128 * SETS, EW = 4 * SETS;       // epilogue threads / warps
+    constexpr int X_OUT_STAGE = x_out_stage(SETS), X_POOL_STAGE = x_pool_stage(SETS);
+    constexpr int CW = 64 / SETS, GW = CW / 16;                    // channels / 16-channel groups per epilogue warp
     constexpr int B_TAP = X_B_TAP / NCTA;                            // this CTA's rows of one (tap, chunk) weight box
     constexpr int B_BLOCK = 3 * B_TAP;
     const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
@@ -81,12 +86,12 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const uint32_t a_base = smem_base;
     const uint32_t b_base = a_base + (uint32_t)a.a_stages * X_A_STAGE;
     const uint32_t stage_off = (uint32_t)a.a_stages * X_A_STAGE + (uint32_t)(chunks * 3) * B_BLOCK;
-    const uint32_t stage_bytes = a.head ? 0u : (uint32_t)a.stage_bufs * (8u * X_OUT_STAGE + (a.pool ? 8u * X_POOL_STAGE : 0u));
+    const uint32_t stage_bytes = a.head ? 0u : (uint32_t)a.stage_bufs * (uint32_t)(EW * X_OUT_STAGE + (a.pool ? EW * X_POOL_STAGE : 0));
     const uint32_t aux_off = stage_off + stage_bytes;
     float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
     float* s_shift = s_scale + 64;
     float* s_head = s_shift + 64;
-    float* s_hpart = s_head + 64;                                     // [2][128] head partial sums of epilogue set 1
+    float* s_hpart = s_head + 64;                                     // [2][SETS - 1][128] head partial sums of sets 1..
     const uint32_t bar_base = smem_base + aux_off + X_AUX_F32 * 4;
     auto full_a = [&](int s) { return bar_base + 8u * s; };
     auto empty_a = [&](int s) { return bar_base + 8u * (X_MAX_A + s); };
@@ -200,8 +205,8 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     } else {
         // ===================================================================== epilogue (warps 3..10; TMEM lane quadrant = warp & 3)
         const int quad = warp & 3;
-        const int et = threadIdx.x - 96;                             // 0..255
-        const int set = (warp - 3) >> 2;                             // channel half owned by this warp
+        const int et = threadIdx.x - 96;
+        const int set = (warp - 3) >> 2;                             // channel slice [CW set, CW set + CW) owned by this warp
         const int r = quad * 2 + (lane >> 4), xh = lane & 15;         // tile row, halo column of this lane's accumulator row
         const bool out_lane = xh >= 1 && xh <= X_TW;
         const int xo = xh - 1;
@@ -211,17 +216,21 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const bool x_first = xh & 1, y_first = !(lane & 16);
         const int x_partner = x_first ? ((lane + 1) & 31) : ((lane + 31) & 31);
         // every epilogue warp stages and stores its own {32 ch, 14 px, 2 rows} box (+ {32, 7, 1} pooled): no CTA-wide barrier
-        const int ew = warp - 3;                                      // 0..7
+        const int ew = warp - 3;
         const uint32_t srow = (uint32_t)((lane >> 4) * X_TW + xo);    // staging row (64 B) of this lane's output pixel
         const uint32_t prow = (uint32_t)(xo >> 1);
         const uint32_t o_stage0 = smem_base + stage_off + (uint32_t)(ew * a.stage_bufs) * X_OUT_STAGE;
-        const uint32_t p_stage0 = smem_base + stage_off + (uint32_t)(8 * a.stage_bufs) * X_OUT_STAGE + (uint32_t)(ew * a.stage_bufs) * X_POOL_STAGE;
+        const uint32_t p_stage0 = smem_base + stage_off + (uint32_t)(EW * a.stage_bufs) * X_OUT_STAGE + (uint32_t)(ew * a.stage_bufs) * X_POOL_STAGE;
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t store_groups = 0;
         const uint32_t tempty_sig0 = PAIR ? mapa_shared(tempty(0), 0) : tempty(0);
         const uint32_t tempty_sig1 = PAIR ? mapa_shared(tempty(1), 0) : tempty(1);
         // accumulator columns of (kx, 16-channel group gl of this warp's channel half)
-        auto acc_col = [&](int kx, int gl) { return (uint32_t)(PAIR ? set * 96 + kx * 32 + gl * 16 : kx * 64 + set * 32 + gl * 16); };
+        const int ch0 = set * CW;
+        auto acc_col = [&](int kx, int gl) {
+            const int c = ch0 + gl * 16;
+            return (uint32_t)(PAIR ? (c >> 5) * 96 + kx * 32 + (c & 31) : kx * 64 + c);
+        };
         for (int w = work_first; w < work_total; w += work_step) {
             const int t = tile_of(w);
             const int img = fast_div(t, a.div_tpi);                 // == n_img for the padding tile of an odd pair
@@ -274,9 +283,9 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(y[i].x, y[i].y);
                 }
-                const uint32_t c0 = ((uint32_t)g & 1u) * 2u;             // 16-byte chunk of this group within the warp's 32 channels
+                const uint32_t c0 = (uint32_t)(g % GW) * 2u;             // 16-byte chunk of this group within the warp's channels
                 if (out_lane) {
-                    const uint32_t rbase = o_stage + srow * 64u, sw = (srow >> 1) & 3u;
+                    const uint32_t rbase = o_stage + srow * (uint32_t)(CW * 2), sw = (GW == 2) ? ((srow >> 1) & 3u) : ((srow >> 2) & 1u);
                     st_shared_v4(rbase + ((c0 ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
                     st_shared_v4(rbase + (((c0 + 1u) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
                 }
@@ -296,15 +305,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                     }
                     if (out_lane) {
                         const uint32_t c16 = c0 + (x_first ? 0u : 1u);
-                        st_shared_v2(p_stage + prow * 64u + ((c16 ^ ((prow >> 1) & 3u)) << 4) + (y_first ? 0u : 8u), m2[0], m2[1]);
+                        const uint32_t psw = (GW == 2) ? ((prow >> 1) & 3u) : ((prow >> 2) & 1u);
+                        st_shared_v2(p_stage + prow * (uint32_t)(CW * 2) + ((c16 ^ psw) << 4) + (y_first ? 0u : 8u), m2[0], m2[1]);
                     }
                 }
             };
 
-            // this warp's 2 x 16 output channels x 3 kx blocks -> registers, then the accumulator is free for the MMA warp
+            // this warp's GW x 16 output channels x 3 kx blocks -> registers, then the accumulator is free for the MMA warp
             uint32_t ra0[16], ra1[16], ra2[16], rb0[16], rb1[16], rb2[16];
             tmem_ld16(t_row + acc_col(0, 0), ra0); tmem_ld16(t_row + acc_col(1, 0), ra1); tmem_ld16(t_row + acc_col(2, 0), ra2);
-            tmem_ld16(t_row + acc_col(0, 1), rb0); tmem_ld16(t_row + acc_col(1, 1), rb1); tmem_ld16(t_row + acc_col(2, 1), rb2);
+            if (GW == 2) { tmem_ld16(t_row + acc_col(0, 1), rb0); tmem_ld16(t_row + acc_col(1, 1), rb1); tmem_ld16(t_row + acc_col(2, 1), rb2); }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
@@ -316,22 +326,26 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                 if (elect_one()) { if (a.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
                 __syncwarp();
             }
-            group(set * 2, ra0, ra1, ra2);
-            group(set * 2 + 1, rb0, rb1, rb2);
+            group(set * GW, ra0, ra1, ra2);
+            if (GW == 2) group(set * GW + 1, rb0, rb1, rb2);
 
-            if (a.head) {                                            // set 1 hands its half of the dot product to set 0
-                float* part = s_hpart + (store_groups & 1u) * 128 + quad * 32 + lane;
-                if (set == 1) *part = head_acc2.x + head_acc2.y;
-                named_bar_sync(2 + quad, 64);                         // the two warps of this lane quadrant
-                if (set == 0 && out_lane && x < a.W && y < a.H && t < a.num_tiles)
-                    a.head_out[((long long)img * a.H + y) * a.W + x] = ((head_acc2.x + head_acc2.y) + *part) + a.head_b[0];
+            if (a.head) {                                            // sets 1.. hand their part of the dot product to set 0
+                float* part = s_hpart + (store_groups & 1u) * (3 * 128) + quad * 32 + lane;
+                if (set > 0) part[(set - 1) * 128] = head_acc2.x + head_acc2.y;
+                named_bar_sync(2 + quad, 32 * SETS);                  // the warps of this lane quadrant
+                if (set == 0 && out_lane && x < a.W && y < a.H && t < a.num_tiles) {
+                    float sum = head_acc2.x + head_acc2.y;
+#pragma unroll
+                    for (int j = 0; j < SETS - 1; ++j) sum += part[j * 128];
+                    a.head_out[((long long)img * a.H + y) * a.W + x] = sum + a.head_b[0];
+                }
                 ++store_groups;
             } else {
                 fence_proxy_async();
                 __syncwarp();
                 if (elect_one()) {                                   // the same lane every time (bulk groups are per thread); uniform
-                    tma_store_4d(&tmOut, o_stage, set * 32, tx * X_TW, ty * X_TH + quad * 2, img);
-                    if (a.pool) tma_store_4d(&tmPool, p_stage, set * 32, tx * (X_TW / 2), ty * (X_TH / 2) + quad, img);
+                    tma_store_4d(&tmOut, o_stage, ch0, tx * X_TW, ty * X_TH + quad * 2, img);
+                    if (a.pool) tma_store_4d(&tmPool, p_stage, ch0, tx * (X_TW / 2), ty * (X_TH / 2) + quad, img);
                     bulk_commit();
                 }
                 ++store_groups;
@@ -348,16 +362,16 @@ conv3x3_dx_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// (n,h,w,64) NHWC bf16 output written in per-warp boxes {32 ch, tw, th, 1}: 64-byte rows, SWIZZLE_64B
-static int make_store_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int tw, int th) {
+// (n,h,w,64) NHWC bf16 output written in per-warp boxes {cw ch, tw, th, 1}: 64-byte rows + SWIZZLE_64B or 32-byte rows + SWIZZLE_32B
+static int make_store_map(CUtensorMap* map, const void* ptr, int n, int h, int w, int tw, int th, int cw) {
     PFN_tmapEncodeTiled enc = get_encode_fn();
     if (!enc) return ADN_ERR_DRIVER;
     cuuint64_t dims[4] = {64u, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
     cuuint64_t strides[3] = {128u, (cuuint64_t)w * 128u, (cuuint64_t)h * w * 128u};
-    cuuint32_t box[4] = {32u, (cuuint32_t)tw, (cuuint32_t)th, 1};
+    cuuint32_t box[4] = {(cuuint32_t)cw, (cuuint32_t)tw, (cuuint32_t)th, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? ADN_OK : ADN_ERR_DRIVER;
 }
@@ -367,6 +381,10 @@ static int make_store_map(CUtensorMap* map, const void* ptr, int n, int h, int w
 // slower -- the same effect conv_halo.cu saw with 32 rows per CTA; only 64-row halves (N = 128 pairs) are fast.  Kept behind the
 // debug hook adn__conv_dx_mode(2) because the parity tests cover it.
 int g_dx_pair = 0;
+// epilogue warp sets of the single-CTA kernel: 2 (32 channels per warp) or 4 (16 per warp); 0 = automatic: four sets where the
+// fused pool makes the epilogue the bottleneck (measured, batch 64: downconv1.3 1.60 -> 1.32 ms), two elsewhere (upconv4.0 2.09 vs
+// 2.26 ms, head conv 1.19 vs 1.28 ms with four: the extra warps take issue slots from the MMA / producer warps)
+int g_dx_sets = 0;
 
 bool conv3x3_dx_eligible(int c0, int c1, int c_out) { return c_out == 64 && (c0 + c1) / 64 <= 2; }
 
@@ -393,22 +411,23 @@ int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w
     if (st != ADN_OK) return st;
     if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, X_PITCH, X_ROWS); else mA1 = mA0;
     if (st != ADN_OK) return st;
+    const int sms = num_sms();
+    const bool pair = g_dx_pair && args.num_tiles >= 2 * sms;
+    const int ncta = pair ? 2 : 1;
+    const int sets = pair ? 2 : (g_dx_sets ? g_dx_sets : (args.pool ? 4 : 2));
     mOut = mA0; mPool = mA0;
     if (!args.head) {
-        st = make_store_map(&mOut, out, n, h, w, X_TW, 2);
+        st = make_store_map(&mOut, out, n, h, w, X_TW, 2, 64 / sets);
         if (st != ADN_OK) return st;
-        if (args.pool) st = make_store_map(&mPool, pool_out, n, h / 2, w / 2, X_TW / 2, 1);
+        if (args.pool) st = make_store_map(&mPool, pool_out, n, h / 2, w / 2, X_TW / 2, 1, 64 / sets);
         if (st != ADN_OK) return st;
     }
 
     constexpr int MAX_DYN = 232448;
     const int AUX = X_AUX_F32 * 4 + (2 * X_MAX_A + 5) * 8 + 16;
-    const int sms = num_sms();
-    const bool pair = g_dx_pair && args.num_tiles >= 2 * sms;
-    const int ncta = pair ? 2 : 1;
     args.stage_bufs = (chunks == 1) ? 2 : 1;
     const int fixed = 1024 + chunks * 3 * (X_B_BLOCK / ncta) +
-                      (args.head ? 0 : args.stage_bufs * (8 * X_OUT_STAGE + (args.pool ? 8 * X_POOL_STAGE : 0))) + AUX;
+                      (args.head ? 0 : args.stage_bufs * 4 * sets * (x_out_stage(sets) + (args.pool ? x_pool_stage(sets) : 0))) + AUX;
     int stages = (MAX_DYN - fixed) / X_A_STAGE;
     if (stages < 2) return ADN_ERR_ARG;
     args.a_stages = stages > X_MAX_A ? X_MAX_A : stages;
@@ -417,22 +436,28 @@ int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w
     if (st != ADN_OK) return st;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
-    cfg.blockDim = dim3(X_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
+    cfg.blockDim = dim3(x_threads(sets)); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = stream;
     if (pair) {
         static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<2>, MAX_DYN, smem_set));
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<2, 2>, MAX_DYN, smem_set));
         const int pairs = (args.num_tiles + 1) / 2;
         cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<2>, mA0, mA1, mB, mOut, mPool, args));
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<2, 2>, mA0, mA1, mB, mOut, mPool, args));
     } else {
-        static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<1>, MAX_DYN, smem_set));
         cfg.gridDim = dim3(args.num_tiles < sms ? args.num_tiles : sms);
         cfg.attrs = nullptr; cfg.numAttrs = 0;
-        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<1>, mA0, mA1, mB, mOut, mPool, args));
+        if (sets == 4) {
+            static unsigned char smem_set[64] = {0};
+            ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<1, 4>, MAX_DYN, smem_set));
+            ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<1, 4>, mA0, mA1, mB, mOut, mPool, args));
+        } else {
+            static unsigned char smem_set[64] = {0};
+            ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_dx_kernel<1, 2>, MAX_DYN, smem_set));
+            ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_dx_kernel<1, 2>, mA0, mA1, mB, mOut, mPool, args));
+        }
     }
     ADN_LAUNCH_CHECK();
     return ADN_OK;

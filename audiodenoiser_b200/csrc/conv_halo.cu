@@ -542,8 +542,11 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
 
 // tuning / debugging hook (not in the public header): 0 disables the CTA-pair kernels
 extern "C" void adn__conv_pair_mode(int mode) { adn::g_pair_mode = mode; }
-// 0: conv_halo kernels only; 1 (default state): conv_dx for the 64-output-channel layers, single CTA; 2: conv_dx as CTA pairs
-extern "C" void adn__conv_dx_mode(int mode) { adn::g_dx_mode = mode != 0; adn::g_dx_pair = mode == 2; }
+// 0: conv_halo kernels only; 1 (default state): conv_dx for the 64-output-channel layers, single CTA, epilogue warp sets chosen per
+// layer; 2: conv_dx as CTA pairs; 3 / 4: single CTA with four / two epilogue warp sets forced
+extern "C" void adn__conv_dx_mode(int mode) {
+    adn::g_dx_mode = mode != 0; adn::g_dx_pair = mode == 2; adn::g_dx_sets = mode == 3 ? 4 : mode == 4 ? 2 : 0;
+}
 
 extern "C" int adn_conv3x3_bn_relu_bf16(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w,
                                         const void* w_packed, int c_out, const float* scale, const float* shift, void* out,

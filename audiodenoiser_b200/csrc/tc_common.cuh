@@ -277,7 +277,7 @@ inline int make_weight_map(CUtensorMap* map, const void* ptr, int n_total, int k
 
 
 // conv_dx.cu: 3x3 conv with 64 output channels, the three horizontal taps folded into the UMMA N dimension
-extern int g_dx_pair;
+extern int g_dx_pair, g_dx_sets;
 bool conv3x3_dx_eligible(int c0, int c1, int c_out);
 int conv3x3_dx(const void* src0, int c0, const void* src1, int c1, int h1, int w1, int n, int h, int w, const void* w_packed,
                const float* scale, const float* shift, float relu_floor, void* out, void* pool_out, const float* head_w,

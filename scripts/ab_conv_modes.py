@@ -19,7 +19,7 @@ lib.adn__conv_dx_mode.restype = None
 net = UNet().eval()
 net.load_state_dict(seeded_state_dict(3))
 x = torch.rand(batch, 1, 257, 1034, device="cuda")
-MODES = (0, 1, 2)
+MODES = (0, 4, 1)
 res = {m: {} for m in MODES}
 with torch.no_grad():
     for rep in range(6):
@@ -34,7 +34,7 @@ with torch.no_grad():
                     d[0] += a.elapsed_time(b); d[1] += 1
             net.profile = None
 tot = {m: 0.0 for m in MODES}
-names = {0: "halo", 1: "dx", 2: "dx-pair"}
+names = {0: "halo", 1: "dx-auto", 2: "dx-pair", 3: "dx-4sets", 4: "dx-2sets"}
 for layer in res[0]:
     ms = {m: res[m][layer][0] / res[m][layer][1] for m in MODES}
     for m in MODES:

@@ -107,11 +107,11 @@ def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
         assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))         # pooling of the stored values is exact
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("n,c0,c1,h,w,relu", [(3, 64, 0, 257, 188, 1), (2, 64, 64, 61, 90, 0), (5, 128, 0, 64, 256, 1)])
 def test_conv3x3_64_output_channels_all_kernels(mode, n, c0, c1, h, w, relu):
     """The 64-output-channel layers have three implementations behind one entry point (debug hook adn__conv_dx_mode): the
-    halo-tile kernel (0), the kx-in-N kernel (1, default) and its CTA-pair variant (2).  All three must agree with F.conv2d,
+    halo-tile kernel (0), the kx-in-N kernel (1, default; 3 and 4 force four and two epilogue warp sets) and its CTA-pair variant (2).  All must agree with F.conv2d,
     with and without the activation, with the fused pool and across a concat."""
     import ctypes
     lib = _lib.load(); s = _lib.stream_ptr()
