@@ -34,6 +34,7 @@ SIGNATURES = {
     "adn_istft_ola_host_f32": (c_int, [P, P, c_uint64, c_int64, c_int64, P]),
     "adn_mix_noise_snr_f32": (c_int, [P, P, c_int64, c_int64, c_float, P, P]),
     "adn_mix_noise_cancel_f32": (c_int, [P, P, c_int64, c_int64, c_int, c_int, c_float, P, P]),
+    "adn_resample_poly_f32": (c_int, [P, c_int64, c_int, c_int64, c_int, c_int, P, c_int, c_int, c_int64, c_int64, P, P]),
     "adn_pack_conv3x3_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
     "adn_pack_convt2x2_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
     "adn_fold_bn_f32": (c_int, [P, P, P, P, P, c_float, c_int, P, P, P]),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libadn_b200.so")
-SOURCES = ["abi.cu", "stft.cu", "istft.cu", "unet_misc.cu", "conv_tc.cu", "conv_halo.cu", "conv_dx.cu", "loss.cu", "train.cu", "wgrad_tc.cu", "noise.cu"]
+SOURCES = ["abi.cu", "stft.cu", "istft.cu", "unet_misc.cu", "conv_tc.cu", "conv_halo.cu", "conv_dx.cu", "loss.cu", "train.cu", "wgrad_tc.cu", "noise.cu", "resample.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

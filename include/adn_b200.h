@@ -108,6 +108,18 @@ int adn_mix_noise_snr_f32(const float* clean, const float* noise, int64_t n_clip
 int adn_mix_noise_cancel_f32(const float* clean, const unsigned char* block_flags, int64_t n_clips, int64_t length, int block,
                              int half, float factor, float* out, void* stream);
 
+/* ------------------------------------------------------------------ resample front-end
+ * The numeric tail of librosa.load(path, sr=8000) (create_train_dataset.py:204,225; create_test_dataset.py:139; test.py:80):
+ * librosa.to_mono + librosa.resample.  x: (n_clips, channels, len_in) float32 planar, mixed down to mono inside the kernel;
+ * y: (n_clips, len_out), len_out = ceil(len_in * up / down).  Polyphase FIR of scipy.signal.resample_poly:
+ *   y[m] = sum_{t < taps} xm[j - t] * table[r * taps_pitch + t],  c = (m + pre_remove) * down, j = c / up, r = c % up.
+ * table: (up, taps_pitch) float32 on the device, 16-byte aligned, rows zero-padded to taps_pitch = a multiple of 4
+ * (audiodenoiser_b200/resample.py builds it: Kaiser beta 5 windowed sinc, half
+ * length 10 * max(up, down), unit DC gain, scaled by up).  The reference's own resampler (soxr_hq inside librosa) is an absent
+ * third-party library with an unspecified filter: parity is against the published scipy algorithm, approximate against soxr. */
+int adn_resample_poly_f32(const float* x, int64_t n_clips, int channels, int64_t len_in, int up, int down, const float* table,
+                          int taps, int taps_pitch, int64_t pre_remove, int64_t len_out, float* y, void* stream);
+
 /* ------------------------------------------------------------------ UNet (code/model.py) */
 
 /* Weight packing, done once per checkpoint load (model.py:53-68 state_dict layout, fp32 on device):

@@ -60,5 +60,16 @@ o = torch.empty_like(c)
 ms = timeit(lambda: adn_noise.mix_noise_snr_batched(c, z, 8.0, out=o))
 b = n * length * 12
 out["mix_noise_snr_4096x16000"] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3)}
+# resample front-end: 3 s clips at 44.1 kHz (mono and stereo) -> 8 kHz; 4 B per input sample and channel + 4 B out
+from audiodenoiser_b200 import resample as adn_resample  # noqa: E402
+for ch in (1, 2):
+    n, length = 1024, 132300
+    xin = torch.rand((n, ch, length), device=dev) - 0.5
+    yo = torch.empty((n, 24000), device=dev)
+    ms = timeit(lambda: adn_resample.resample_batched(xin, 44100, 8000, out=yo))
+    b = n * (4 * ch * length + 4 * 24000)
+    out[f"resample_44k1_to_8k_{n}x{ch}x{length}"] = {"ms": round(ms, 4), "GBps": round(b / ms / 1e6), "frac": round(b / ms / 1e6 / peak, 3),
+                                                      "audio_s_per_s": round(n * 3.0 / (ms * 1e-3))}
+    del xin, yo
 for k, v in out.items():
     print(k, v)
