@@ -9,18 +9,22 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib, spectral
+from . import _lib, resample, spectral
 from .model import UNet
 
 
 class Denoiser:
-    def __init__(self, model: UNet, center: bool = True, seed: int = 0, use_graph: bool = True, phase: str = "random"):
+    def __init__(self, model: UNet, center: bool = True, seed: int = 0, use_graph: bool = True, phase: str = "random",
+                 input_sr: int | None = None):
         """phase="random" is the reference's reconstruction (test.py:36: a fresh random phase).  phase="noisy" (opt-in, SURVEY 8f
-        row 4) reuses the phase of the noisy input's STFT -- audibly better, but NOT what the reference computes."""
+        row 4) reuses the phase of the noisy input's STFT -- audibly better, but NOT what the reference computes.
+        input_sr: native sample rate of the input clips; when it is not 8000 the clips -- (N, L) mono or (N, C, L) planar -- are
+        mixed down and resampled to 8 kHz on the device first (the tail of librosa.load(sr=8000), test.py:80)."""
         _lib.require_cuda()
         if phase not in ("random", "noisy"):
             raise ValueError("phase must be 'random' or 'noisy'")
         self.phase = phase
+        self.input_sr = int(input_sr) if input_sr else None
         self.model = model.eval()
         self.center = bool(center)
         self.seed = int(seed)
@@ -35,6 +39,8 @@ class Denoiser:
         buffers: they are overwritten by the next call with the same shape."""
         if wave.dim() == 1:
             wave = wave.unsqueeze(0)
+        if wave.dim() == 3 and not self.input_sr:
+            raise ValueError("multi-channel input needs input_sr (the mono mix is part of the resample front-end)")
         if wave.dtype != torch.float32:
             wave = wave.float()
         if not self.use_graph:
@@ -59,6 +65,8 @@ class Denoiser:
         return g["audio"]
 
     def _run(self, wave, phasor):
+        if self.input_sr and (self.input_sr != resample.SAMPLE_RATE or wave.dim() == 3):
+            wave = resample.resample_batched(wave, self.input_sr, resample.SAMPLE_RATE)
         if self.phase == "noisy" and phasor is None:
             spec = spectral.stft_complex_batched(wave, self.center)
             mag = spec.abs()

@@ -90,3 +90,20 @@ def test_noisy_phase_reconstruction_opt_in(net):
     b = Denoiser(net, phase="noisy", use_graph=True).denoise(x)
     assert a.shape == (2, 23936) and torch.equal(a, b)
     assert not torch.equal(a, Denoiser(net, seed=1, use_graph=False).denoise(x))
+
+
+def test_native_rate_input_is_resampled_on_the_device(net):
+    """Denoiser(input_sr=44100): stereo 44.1 kHz clips -> mono 8 kHz inside the captured graph; the result
+    equals the 8 kHz pipeline fed with the front-end's own output, and the spectrogram has the reference's (257, 188) shape."""
+    from audiodenoiser_b200 import resample as rs
+    g = torch.Generator().manual_seed(11)
+    native = (torch.rand((2, 2, 3 * 44100), generator=g) - 0.5).to(dev())
+    for use_graph in (False, True):
+        front = Denoiser(net, center=True, seed=5, use_graph=use_graph, input_sr=44100)
+        audio, mag, _ = front.denoise(native, return_spectrograms=True)
+        assert mag.shape == (2, 257, 188) and audio.shape == (2, 128 * 187)
+        plain = Denoiser(net, center=True, seed=5, use_graph=False)
+        ref_audio, ref_mag, _ = plain.denoise(rs.resample_batched(native, 44100, 8000), return_spectrograms=True)
+        assert torch.equal(mag, ref_mag) and torch.equal(audio, ref_audio)
+    with pytest.raises(ValueError):
+        Denoiser(net, use_graph=False).denoise(native)
