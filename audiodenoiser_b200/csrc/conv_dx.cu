@@ -17,14 +17,14 @@
 //               SWIZZLE_128B tile of 128 rows at base + ky * 2048 B.
 //   B operand   the packed weights [co][tap][ci] (adn_pack_conv3x3_weight_bf16) loaded ONCE per CTA as 9 * chunks boxes {64, 64}
 //               into [chunk][ky][kx][co] order: one (chunk, ky) operand = 192 consecutive rows.
-//   roles       warp 0 A producer, warp 1 UMMA issuer, warp 2 weight loader + TMEM allocator, warps 3..10 epilogue: two sets of
-//               four warps (one per TMEM lane quadrant), set s owning output channels [32 s, 32 s + 32)
+//   roles       warp 0 A producer, warp 1 UMMA issuer, warp 2 weight loader + TMEM allocator, then SETS x 4 epilogue warps: set s
+//               owns output channels [64 s / SETS, 64 (s + 1) / SETS) of all four TMEM lane quadrants (SETS = 2, or 4 for the
+//               pool-fused layer whose epilogue is the bottleneck)
 //               (tcgen05.ld -> neighbour-lane sum -> fp32 scale/shift -> ReLU -> bf16 -> the warp's own swizzled staging -> its own
-//               TMA store of a {32 ch, 14 px, 2 rows} box, + fused 2x2 max-pool {32, 7, 1} | fused 1x1 head): no CTA-wide
-//               barrier anywhere in the tile loop.  Two TMEM accumulators, released as soon
-//               as a warp holds its columns in registers.  With K = 576 these layers are epilogue-bound: one warp per
-//               scheduler could not hide the shuffle / TMEM latencies (measured 1.98 ms for downconv1's second conv with one
-//               set).
+//               TMA store of a {32 | 16 ch, 14 px, 2 rows} box, + fused 2x2 max-pool {., 7, 1} | fused 1x1 head): no CTA-wide
+//               barrier anywhere in the tile loop.  Two TMEM accumulators, each released as soon as a warp holds its columns
+//               in registers.  With K = 576 these layers are epilogue-bound: one warp per scheduler could not hide the shuffle /
+//               TMEM latencies (measured 1.98 ms for downconv1's second conv with 4 epilogue warps, 1.60 with 8, 1.32 with 16).
 #include "tc_common.cuh"
 
 namespace adn {
