@@ -515,7 +515,8 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     // SM pair still gets work
     const int num_m = n * args.tiles_x * args.tiles_y;
     // measured (variant B, batch 64): 128-wide layers with >= 2 input chunks gain 8-32 % (upconv3.0: 1 171 -> 1 548 TFLOP/s);
-    // 64-wide layers LOSE 30 % in pair mode (a 256x64 UMMA is too short to amortise), so they stay single-CTA
+    // 64-wide layers LOSE 30 % in pair mode (a 256x64 UMMA is too short to amortise), so they stay single-CTA; so does the 128-wide
+    // layer with ONE input chunk (downconv2.0, K = 576: 0.65 -> 0.89 ms as a pair)
     const bool pair = g_pair_mode && block_n == 128 && (c0 + c1) >= 128 && args.n_blocks == 1 && num_m >= 2 * (num_sms() / 2);
     st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), pair ? block_n / 2 : block_n);
     if (st != ADN_OK) return st;
