@@ -21,6 +21,7 @@ P = c_void_p
 # name -> (restype, argtypes); mirrors include/adn_b200.h one to one
 SIGNATURES = {
     "adn_version": (c_int, []),
+    "adn_source_hash": (c_char_p, []),
     "adn_error_string": (c_char_p, [c_int]),
     "adn_last_cuda_error": (c_int, []),
     "adn_device_check": (c_int, []),
@@ -80,26 +81,57 @@ class AdnError(RuntimeError):
     pass
 
 
+def _built_hash() -> str | None:
+    """The source hash stamped into the .so on disk, read WITHOUT loading it into this process (a loaded library cannot be
+    replaced): a throw-away python reads ``adn_source_hash()``."""
+    import subprocess
+    import sys
+    code = ("import ctypes,sys;l=ctypes.CDLL(sys.argv[1]);f=l.adn_source_hash;f.restype=ctypes.c_char_p;print(f().decode())")
+    try:
+        r = subprocess.run([sys.executable, "-c", code, LIB_PATH], capture_output=True, text=True, timeout=120)
+    except Exception:  # noqa: BLE001
+        return None
+    return r.stdout.strip() if r.returncode == 0 and r.stdout.strip() else None
+
+
 def load(build_if_missing: bool = True):
-    """Load (once) and return the ctypes handle.  Raises AdnError when the native library is unavailable."""
+    """Load (once) and return the ctypes handle.  Raises AdnError when the native library is unavailable, or when it was
+    built from other sources than the ones beside it and cannot be rebuilt (no silent use of a stale binary)."""
     global _lib
     if _lib is not None:
         return _lib
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH) and build_if_missing:
+        from . import build as _build
+        want = _build.source_hash()
+        stamp = os.path.join(_build.BUILD, "source_hash.txt")
+        stamped = open(stamp).read().strip() if os.path.exists(stamp) else None
+        fresh = os.path.exists(LIB_PATH) and stamped == want and os.path.getmtime(LIB_PATH) >= os.path.getmtime(stamp) - 1.0
+        if not fresh and os.path.exists(LIB_PATH) and _built_hash() == want:
+            fresh = True
+        if not fresh and build_if_missing:
             try:
-                from . import build as _build
-                _build.build()
+                _build.build()                       # mtime- and hash-incremental; a no-op when everything is current
             except Exception as exc:  # noqa: BLE001
-                raise AdnError(f"libadn_b200.so is missing and could not be built: {exc}") from exc
+                raise AdnError(f"libadn_b200.so is missing or stale and could not be built: {exc}") from exc
         if not os.path.exists(LIB_PATH):
             raise AdnError(f"{LIB_PATH} not found: run `python -m audiodenoiser_b200.build` (no CPU fallback exists)")
+        try:
+            import torch  # noqa: F401  (brings libcudart.so.12 into the process: the library links the shared runtime)
+        except Exception:  # noqa: BLE001
+            pass
         try:
             lib = ctypes.CDLL(LIB_PATH)
         except OSError as exc:
             raise AdnError(f"cannot load {LIB_PATH}: {exc}") from exc
+        try:
+            lib.adn_source_hash.restype = c_char_p
+            have = lib.adn_source_hash().decode()
+        except AttributeError:
+            have = "missing"
+        if have != want:
+            raise AdnError(f"{LIB_PATH} was built from other sources (hash {have}, sources {want}): run `python -m audiodenoiser_b200.build`")
         for name, (res, args) in SIGNATURES.items():
             try:
                 fn = getattr(lib, name)

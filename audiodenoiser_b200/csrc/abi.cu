@@ -26,7 +26,12 @@ int check_device() {
 
 }  // namespace adn
 
-extern "C" int adn_version(void) { return 100; }
+extern "C" int adn_version(void) { return 200; }
+
+#ifndef ADN_SOURCE_HASH
+#define ADN_SOURCE_HASH "unstamped"
+#endif
+extern "C" const char* adn_source_hash(void) { return ADN_SOURCE_HASH; }
 
 extern "C" const char* adn_error_string(int status) {
     switch (status) {

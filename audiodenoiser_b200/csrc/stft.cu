@@ -71,18 +71,31 @@ __device__ __forceinline__ void stft_stage(float* buf, const float* __restrict__
     }
     if (length <= 0) src = dummy;                        // nothing is read (src-size 0), but keep the address valid
     const int g_last = (length - 1) & ~1;                // clamp target: even (8-byte aligned when src is) and in range
+    if (al8) {
+        // edge tiles (zero padding in front of the clip, ragged tail): same thread -> (row, column pair) map as the interior path,
+        // with a per-row byte count.  s0 is a multiple of 128 and the pair index is even, so a pair never straddles sample 0;
+        // at the tail it holds 2, 1 or 0 valid samples (cp.async zero-fills the rest).
+        const int r0 = tid >> 6;
+        const int g0 = s0 + r0 * ADN_HOP + ((tid & 63) << 1);
+        const uint32_t dst = st_smem_u32(buf + r0 * ST_ROW_STRIDE + ((tid & 63) << 1));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            if (r0 + 4 * i < rows) {
+                const int g = g0 + 4 * i * ADN_HOP;
+                const int nvalid = min(max(length - g, 0), 2);
+                cp_async8(dst + i * 4 * ST_ROW_STRIDE * 4, src + min(max(g, 0), max(g_last, 0)), g < 0 ? 0 : 4 * nvalid);
+            }
+        }
+        return;
+    }
     for (int p = tid; p < rows * 64; p += STFT_THREADS) {
         const int row = p >> 6, c = (p & 63) << 1;
         const int g = s0 + row * ADN_HOP + c;
         const uint32_t dst = st_smem_u32(buf + row * ST_ROW_STRIDE + c);
         const bool ok0 = (unsigned)g < (unsigned)length, ok1 = (unsigned)(g + 1) < (unsigned)length;
         const float* sp = src + max(0, min(g, g_last));
-        if (al8) {                                       // g is even: ok1 implies ok0
-            cp_async8(dst, sp, ok0 ? (ok1 ? 8 : 4) : 0);
-        } else {
-            cp_async4(dst, sp, ok0 ? 4 : 0);
-            cp_async4(dst + 4, ok1 ? sp + 1 : sp, ok1 ? 4 : 0);
-        }
+        cp_async4(dst, sp, ok0 ? 4 : 0);
+        cp_async4(dst + 4, ok1 ? sp + 1 : sp, ok1 ? 4 : 0);
     }
 }
 
@@ -187,6 +200,35 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
         };
         const float4* twa = reinterpret_cast<const float4*>(s_tw512 + a * 16);        // W512^(a + 16 k2), two per load
         const float4* twb = reinterpret_cast<const float4*>(s_tw512 + 8 * 16);        // W512^(8 + 16 k2) (warp 0)
+        if (!COMPLEX_OUT && !CROP && w != 0) {
+            // Hot path (|STFT| only): every pair is stored as soon as it is split -- the 32 stores and square roots of a thread are
+            // spread over the split arithmetic instead of queueing behind it (STG / MUFU were 26 % of pass 2's stall samples), and the
+            // two row pointers advance by one 64-bit add per store (rows a + 16 k2 upwards, rows b + 16 k2 downwards from k2 = 15)
+            // instead of a multiply-wide plus two adds.
+            const long long row0 = ((long long)cur_clip * ADN_N_BINS) * n_frames + cur_t0 + lane;
+            const long long step = 16LL * n_frames;
+            float* pa = out + row0 + (long long)a * n_frames;
+            float* pb = out + row0 + (long long)(b + 240) * n_frames;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                                             // 256 - k = b + 16 (15 - k2)
+                const float4 q = twa[j];
+                split(make_float2(q.x, q.y), A[2 * j], B[15 - 2 * j]);
+                split(make_float2(q.z, q.w), A[2 * j + 1], B[14 - 2 * j]);
+                const float m0 = sqrt_approx(fmaf(A[2 * j].x, A[2 * j].x, A[2 * j].y * A[2 * j].y));
+                const float m1 = sqrt_approx(fmaf(B[15 - 2 * j].x, B[15 - 2 * j].x, B[15 - 2 * j].y * B[15 - 2 * j].y));
+                const float m2 = sqrt_approx(fmaf(A[2 * j + 1].x, A[2 * j + 1].x, A[2 * j + 1].y * A[2 * j + 1].y));
+                const float m3 = sqrt_approx(fmaf(B[14 - 2 * j].x, B[14 - 2 * j].x, B[14 - 2 * j].y * B[14 - 2 * j].y));
+                if (live) {
+                    __stcs(pa, m0);
+                    __stcs(pb, m1);
+                    __stcs(pa + step, m2);
+                    __stcs(pb - step, m3);
+                }
+                pa += 2 * step;
+                pb -= 2 * step;
+            }
+            continue;                                            // next tile (the loop's first barrier orders `work`)
+        }
         if (w != 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {                                             // 256 - k = b + 16 (15 - k2)

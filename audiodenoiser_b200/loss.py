@@ -2,9 +2,9 @@
 
 Same constructor (no arguments), same attributes (``w_stft = 0.4``, ``w_mel = 0.4``, ``w_l1 = 0.2``), same call:
 ``total, stft, mel, l1 = criterion(pred, target)`` with (B, 1, F, T) float32 tensors, returning four 0-dim tensors on the
-inputs' device (test.py:118-122, train.py:68,85).  The arithmetic runs in the CUDA kernels of csrc/loss.cu through
+inputs' device (test.py:118-122 passes host tensors, train.py:68,85 CUDA tensors).  The arithmetic runs in the CUDA kernels of csrc/loss.cu through
 ``adn_combined_loss_f32``.  When ``pred`` requires grad the four values are part of the autograd graph: ``loss.backward()``
-(train.py:69) runs ``adn_combined_loss_backward_f32``.  No CPU fallback.
+(train.py:69) runs ``adn_combined_loss_backward_f32``.  No CPU code path (host tensors are staged to the GPU and back).
 """
 from __future__ import annotations
 
@@ -44,7 +44,7 @@ class _LossKernel:
     def __call__(self, pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         torch_ = _lib.require_cuda()
         if not (isinstance(pred, torch_.Tensor) and pred.is_cuda and target.is_cuda):
-            raise _lib.AdnError("CombinedPerceptualLoss needs CUDA tensors (no CPU fallback)")
+            raise _lib.AdnError("the loss kernels take CUDA tensors (host tensors are staged by CombinedPerceptualLoss.forward)")
         if pred.shape != target.shape:
             raise ValueError("pred and target must have the same shape")
         if pred.dim() == 3:                       # (B, F, T) is accepted as (B, 1, F, T)
@@ -106,7 +106,17 @@ class _LossFunction(torch.autograd.Function):
 
 
 def _values(pred, target):
-    if torch.is_grad_enabled() and isinstance(pred, torch.Tensor) and pred.requires_grad:
+    """(total, stft, mel, l1) as a 4-vector on pred's device.  HOST tensors -- what test.py:119-121 passes -- are copied to the
+    current GPU, reduced by the same kernels, and the four values are copied back (host in / host out, not a CPU code path)."""
+    _lib.require_cuda()
+    if not isinstance(pred, torch.Tensor) or not isinstance(target, torch.Tensor):
+        raise TypeError("pred and target must be torch tensors")
+    if not pred.is_cuda:
+        dev = target.device if target.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        return _values(pred.to(dev), target.to(dev)).cpu()
+    if not target.is_cuda:
+        target = target.to(pred.device)
+    if torch.is_grad_enabled() and pred.requires_grad:
         return _LossFunction.apply(pred, target)
     return _KERNEL(pred, target)
 

@@ -7,7 +7,8 @@ The module holds fp32 master parameters in the reference layout; a packed copy (
 scale/shift) is rebuilt whenever they change.  In ``train()`` mode ``forward`` runs the batch-statistics kernels of
 ``training.TrainEngine`` and returns a tensor that is part of the autograd graph: ``loss.backward()`` runs the hand-written
 backward kernels and deposits ``.grad`` on every parameter, so the reference's train_one_epoch body (train.py:65-72) works
-unchanged with any torch optimizer.  No CPU path: non-CUDA input raises.
+unchanged with any torch optimizer.  No CPU code path: a host tensor (test.py:100,113) is copied to the GPU, processed by the
+same kernels and copied back; without a CUDA device every call raises.
 """
 from __future__ import annotations
 
@@ -62,7 +63,11 @@ class UNet(nn.Module):
         super().__init__()
         if in_channels != 1 or num_classes != 1:
             raise ValueError("the B200 build is specialised to the reference's UNet(in_channels=1, num_classes=1)")
-        g = torch.Generator().manual_seed(0)
+        # Same initialisation as the reference's nn modules, drawn from the GLOBAL torch RNG in the same order and with the same
+        # calls (nn.Conv2d / nn.ConvTranspose2d.reset_parameters: kaiming_uniform_(a=sqrt(5)) weights, U(+-1/sqrt(fan_in)) biases;
+        # BatchNorm2d ones / zeros): torch.manual_seed(s); UNet() yields the state_dict the reference's UNet() would.
+        import math
+        last_fan_in = 1
         for key, (shape, dtype) in state_dict_spec().items():
             leaf = key.rsplit(".", 1)[1]
             is_buffer = leaf in ("running_mean", "running_var", "num_batches_tracked")
@@ -72,11 +77,13 @@ class UNet(nn.Module):
             elif is_bn:
                 t = torch.ones(shape) if leaf in ("weight", "running_var") else torch.zeros(shape)
             elif len(shape) == 4:
-                fan_in = shape[1] * shape[2] * shape[3]
-                bound = (1.0 / fan_in) ** 0.5                      # same scale as nn.Conv2d's default init
-                t = (torch.rand(shape, generator=g) * 2 - 1) * bound
-            else:
-                t = torch.zeros(shape)                             # conv / conv-transpose / head bias
+                t = torch.empty(shape)
+                nn.init.kaiming_uniform_(t, a=math.sqrt(5))
+                last_fan_in = shape[1] * shape[2] * shape[3]
+            else:                                                  # the bias that follows its conv / conv-transpose / head weight
+                bound = 1.0 / math.sqrt(last_fan_in)
+                t = torch.empty(shape)
+                nn.init.uniform_(t, -bound, bound)
             _attach(self, key, t, is_buffer)
         self._packed = None
         self._packed_key = None
@@ -230,24 +237,31 @@ class UNet(nn.Module):
             self._engine.set_hyperparameters(**optimizer_kwargs)
         return self._engine
 
+    def _compute_device(self):
+        """Where a HOST input is processed: the parameters' device when the module was moved to a GPU, else the current one."""
+        p = next(self.parameters())
+        return p.device if p.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
     def forward(self, x):
         """UNet.forward, model.py:70-94: eval() -> running-statistics BatchNorm folded into the conv epilogues;
-        train() -> batch-statistics BatchNorm, differentiable (train.py:67,69)."""
+        train() -> batch-statistics BatchNorm, differentiable (train.py:67,69).
+
+        The result lives on the input's device, as with the reference module.  A HOST tensor -- what test.py:100,113 feeds
+        (`model` is never moved off the CPU there) -- is staged through pinned memory to the GPU, run through the same
+        kernels, and the result is copied back to a host tensor: host in / host out is not a CPU code path."""
         _lib.require_cuda()
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError("expected (N, 1, F, T) input")
         if not x.is_cuda:
-            raise _lib.AdnError("UNet.forward needs a CUDA tensor (no CPU fallback); move the input with .cuda()")
+            dev = self._compute_device()
+            y = self.forward(_host_to_device(x, dev))
+            return y.cpu()
         if self.training:
-            if x.dim() != 4 or x.shape[1] != 1:
-                raise ValueError("expected (N, 1, F, T) input")
             eng = self.train_engine(x.device)
             eng.refresh_if_parameters_changed()
             if torch.is_grad_enabled():
                 return _TrainForward.apply(x, eng, *[p for _, p in self.named_parameters()])
             return eng.forward(x)
-        if not x.is_cuda:
-            raise _lib.AdnError("UNet.forward needs a CUDA tensor (no CPU fallback); move the input with .cuda()")
-        if x.dim() != 4 or x.shape[1] != 1:
-            raise ValueError("expected (N, 1, F, T) input")
         x = x.float().contiguous()
         with torch.cuda.device(x.device), torch.no_grad():
             pk = self.packed(x.device)
@@ -255,3 +269,11 @@ class UNet(nn.Module):
             for i in range(0, x.shape[0], _MAX_CHUNK):
                 self._forward_chunk(x[i:i + _MAX_CHUNK], out[i:i + _MAX_CHUNK], pk)
         return out
+
+
+def _host_to_device(x: torch.Tensor, dev) -> torch.Tensor:
+    """Host tensor -> device, through a pinned staging copy when the source is pageable and large (a pageable cudaMemcpy is
+    staged by the driver in small chunks); keeps autograd history (``.to`` is differentiable)."""
+    if x.requires_grad or x.numel() < (1 << 16) or x.is_pinned():
+        return x.to(dev, non_blocking=x.is_pinned())
+    return x.float().contiguous().pin_memory().to(dev, non_blocking=True)

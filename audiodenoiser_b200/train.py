@@ -1,7 +1,7 @@
 """Drop-in for the hot-path functions of the reference's code/train.py: ``train_one_epoch`` (train.py:61-76) and
 ``validate_one_epoch`` (train.py:78-90), same positional arguments and return value (the epoch's mean total loss).
 
-``train_one_epoch`` is the reference's body verbatim -- it works because ``audiodenoiser_b200.model.UNet`` (train mode) and
+``train_one_epoch`` is the reference's body verbatim (plus the deferred loader transform for worker batches) -- it works because ``audiodenoiser_b200.model.UNet`` (train mode) and
 ``audiodenoiser_b200.loss.CombinedPerceptualLoss`` are autograd nodes backed by the B200 kernels, so ``loss.backward()``,
 ``clip_grad_norm_`` and any torch optimizer behave as with the reference modules.  ``train_one_epoch_fused`` is the fast path:
 the whole step (forward, loss, backward, DDP all-reduce, clip, AdamW) on the engine's kernels, one CUDA-graph replay per batch.
@@ -12,13 +12,28 @@ from __future__ import annotations
 
 import torch
 
+from .data_loader import SpectrogramDataset, finish_on_device
+
+
+def _deferred_transform(dataloader) -> bool:
+    """True when the batches come out of DataLoader WORKER processes over a ``SpectrogramDataset`` (train.py:118-119 uses
+    num_workers=4): the workers only crop / pad, and the float16 round trip of data_loader.py:41-42 has to be applied here, on
+    the device (see data_loader.py's module docstring)."""
+    ds = getattr(dataloader, "dataset", None)
+    while hasattr(ds, "dataset"):                 # random_split (train.py:114) wraps the dataset in Subset
+        ds = ds.dataset
+    return isinstance(ds, SpectrogramDataset) and getattr(dataloader, "num_workers", 0) > 0
+
 
 def train_one_epoch(model, dataloader, criterion, optimizer, device, writer=None, epoch=0):
     """train.py:61-76."""
     model.train()
     total_loss = 0.0
+    finish = _deferred_transform(dataloader)
     for noisy, clean in dataloader:
         noisy, clean = noisy.to(device), clean.to(device)            # train.py:65
+        if finish:
+            noisy, clean = finish_on_device(noisy), finish_on_device(clean)
         optimizer.zero_grad()                                        # :66
         outputs = model(noisy)                                       # :67
         loss, _, _, _ = criterion(outputs, clean)                    # :68
@@ -36,9 +51,12 @@ def validate_one_epoch(model, dataloader, criterion, device, writer=None, epoch=
     """train.py:78-90."""
     model.eval()
     total_loss = 0.0
+    finish = _deferred_transform(dataloader)
     with torch.no_grad():
         for noisy, clean in dataloader:
             noisy, clean = noisy.to(device), clean.to(device)
+            if finish:
+                noisy, clean = finish_on_device(noisy), finish_on_device(clean)
             outputs = model(noisy)
             loss, _, _, _ = criterion(outputs, clean)
             total_loss += loss.item()
@@ -54,8 +72,12 @@ def train_one_epoch_fused(model, dataloader, device, lr=1e-4, writer=None, epoch
     model.train()
     engine = model.train_engine(device, lr=lr)
     total = torch.zeros((), dtype=torch.float32, device=engine.device)
+    finish = _deferred_transform(dataloader)
     for noisy, clean in dataloader:
-        losses = engine.train_step_graphed(noisy.to(engine.device, non_blocking=True), clean.to(engine.device, non_blocking=True))
+        noisy, clean = noisy.to(engine.device, non_blocking=True), clean.to(engine.device, non_blocking=True)
+        if finish:
+            noisy, clean = finish_on_device(noisy), finish_on_device(clean)
+        losses = engine.train_step_graphed(noisy, clean)
         total += losses[0]
     avg_loss = float(total) / len(dataloader)
     if writer is not None:

@@ -60,7 +60,7 @@ class TrainEngine:
         self.lib = _lib.load()
         self.device = torch_.device("cuda", torch_.cuda.current_device()) if device is None else torch_.device(device)
         self.model = model.to(self.device)
-        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = float(lr), tuple(betas), float(eps), float(weight_decay), float(max_norm)
+        self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = float(lr), tuple(float(b) for b in betas), float(eps), float(weight_decay), float(max_norm)
         self.group = process_group
         self.step_count = 0
         self.launch_count = 0
@@ -115,12 +115,14 @@ class TrainEngine:
         self.model._engine = self
 
     def set_hyperparameters(self, lr=None, betas=None, eps=None, weight_decay=None, max_norm=None):
+        before = (self.lr, self.betas, self.eps, self.weight_decay, self.max_norm)
         if lr is not None: self.lr = float(lr)
-        if betas is not None: self.betas = tuple(betas)
+        if betas is not None: self.betas = tuple(float(b) for b in betas)
         if eps is not None: self.eps = float(eps)
         if weight_decay is not None: self.weight_decay = float(weight_decay)
         if max_norm is not None: self.max_norm = float(max_norm)
-        self._graph = None                       # the values are baked into a captured step
+        if (self.lr, self.betas, self.eps, self.weight_decay, self.max_norm) != before:
+            self._graph = None                   # the values are baked into a captured step; unchanged values keep the graph
 
     def _versions(self):
         return tuple(int(p._version) for p in self.model.parameters())
@@ -429,4 +431,8 @@ class TrainEngine:
         g["graph"].replay()
         self.step_count += 1
         self.launch_count += g["launches"]
+        # The replay updated the parameters and the BatchNorm running statistics through raw device pointers: no tensor version
+        # counter moved, so the module's eval-mode cache (packed bf16 weights + folded BN scale / shift, keyed on versions) must be
+        # dropped by hand, or model.eval() after graphed steps would run with the weights of the last eager step.
+        self.model._packed = None
         return g["out"]

@@ -47,6 +47,9 @@ typedef enum {
 } adn_status;
 
 int adn_version(void);
+/* First 16 hex digits of the sha256 over the sources (csrc/ and include/) this binary was built from; the Python binding refuses a
+ * library whose hash differs from the sources beside it (audiodenoiser_b200/build.py:source_hash). */
+const char* adn_source_hash(void);
 const char* adn_error_string(int status);
 int adn_last_cuda_error(void);
 /* ADN_OK iff the current CUDA device can run this library (sm_100). */
@@ -151,6 +154,7 @@ int adn_conv3x3_bn_relu_head_f32(const void* src0, int c0, const void* src1, int
                                  int n, int h, int w, const void* w_packed, int c_out,
                                  const float* scale, const float* shift,
                                  const float* head_w, const float* head_b, float* out_f32, void* stream);
+
 
 /* ConvTranspose2d(k=2,s=2) + bias as a tcgen05 GEMM with a pixel-shuffle store (model.py:38,43):
  * src (n,h,w,c_in) -> out (n,2h,2w,c_out).  bias: (c_out) fp32. */

@@ -11,3 +11,6 @@ for k, v in d["kernels"].items():
         print(" ", k, {a: (round(b, 4) if isinstance(b, float) else b) for a, b in v.items()})
 for k, v in d["kernels"].get("layers", {}).items():
     print("   ", k, round(v["ms"], 3), round(v["TFLOPs"] or 0))
+for k in ("parity", "gather_check", "cpu_baseline", "clocks"):
+    if d.get(k) is not None:
+        print(k, d[k])

@@ -53,6 +53,38 @@ def test_dataset_pairs_and_items(tmp_path):
         SpectrogramDataset(str(tmp_path))
 
 
+def test_dataloader_with_worker_processes(tmp_path):
+    """train.py:118-119 wraps the dataset in DataLoader(num_workers=4, pin_memory=True).  Worker processes have no CUDA context:
+    they only crop / pad (no arithmetic) and the float16 round trip is applied by finish_on_device in the consuming process;
+    the finished batch is bit-identical to the main-process items, and finishing is idempotent."""
+    from torch.utils.data import DataLoader, random_split
+    from audiodenoiser_b200.data_loader import finish_on_device
+    from audiodenoiser_b200.train import _deferred_transform
+    rng = np.random.default_rng(1)
+    for k in range(6):
+        np.save(tmp_path / f"noisy_white_chunk_{k}.npy", (np.abs(rng.standard_normal((257, 122))) * 3).astype(np.float32))
+        np.save(tmp_path / f"clean_white_chunk_{k}.npy", (np.abs(rng.standard_normal((257, 40))) * 3).astype(np.float32))
+    ds = SpectrogramDataset(str(tmp_path))
+    torch.cuda.init()                                         # the parent holds a CUDA context, as train.py:122 does before iterating
+    loader = DataLoader(ds, batch_size=3, shuffle=False, num_workers=2, pin_memory=True)
+    assert _deferred_transform(loader) and not _deferred_transform(DataLoader(ds, batch_size=3))
+    sub, _ = random_split(ds, [4, 2])
+    assert _deferred_transform(DataLoader(sub, batch_size=2, num_workers=2))
+    seen = 0
+    for noisy, clean in loader:
+        assert noisy.shape == (3, 1, 256, 64) and not noisy.is_cuda
+        fn, fc = finish_on_device(noisy), finish_on_device(clean)
+        assert fn.is_cuda and torch.equal(finish_on_device(fn), fn)
+        for j in range(3):
+            mn, mc = ds[seen + j]                             # main process: the CUDA transform inside __getitem__
+            assert torch.equal(fn[j].cpu(), mn) and torch.equal(fc[j].cpu(), mc)
+        seen += 3
+    assert seen == 6
+    strict = SpectrogramDataset(str(tmp_path), strict_workers=True)
+    with pytest.raises(RuntimeError, match="num_workers=0"):
+        next(iter(DataLoader(strict, batch_size=2, num_workers=1)))
+
+
 @pytest.mark.parametrize("length,center", [(16000, False), (24000, True), (4000, False), (8100, True)])
 def test_stft_second_output_is_the_loader_transform(length, center):
     """the STFT kernel's second output == SpectrogramDataset's transform (float16 round trip, crop / zero-pad

@@ -56,7 +56,22 @@ def test_filterbank_and_validation():
     assert torch.equal(mel_filterbank(), loss_oracle.mel_filterbank().float())
     crit = CombinedPerceptualLoss()
     assert (crit.w_stft, crit.w_mel, crit.w_l1) == (0.4, 0.4, 0.2)
-    with pytest.raises(_lib.AdnError):
-        crit(torch.rand(1, 1, 8, 64), torch.rand(1, 1, 8, 64))
+    with pytest.raises(ValueError):
+        crit(torch.rand(1, 1, 8, 64), torch.rand(1, 1, 9, 64))                                     # shape mismatch (host tensors)
     with pytest.raises(ValueError):
         crit(torch.rand(1, 1, 8, 16, device="cuda"), torch.rand(1, 1, 8, 16, device="cuda"))      # T <= 31: reflect pad impossible
+
+
+def test_host_tensors_in_host_scalars_out(golden_dir):
+    """test.py:119-121 passes CPU tensors and calls .item() on the four results: host in -> the same kernels -> host out."""
+    z = np.load(os.path.join(golden_dir, "loss_test.npz"))
+    crit = CombinedPerceptualLoss()
+    p, t = torch.from_numpy(z["pred"].astype(np.float32)), torch.from_numpy(z["target"].astype(np.float32))
+    host = crit(p, t)
+    devv = crit(p.cuda(), t.cuda())
+    assert all(not v.is_cuda and v.dim() == 0 for v in host)
+    for a, b in zip(host, devv):
+        assert float(a) == float(b)
+    # mixed placement (prediction on the GPU, target still on the host) follows the prediction
+    mixed = crit(p.cuda(), t)
+    assert mixed[0].is_cuda and float(mixed[0]) == float(devv[0])

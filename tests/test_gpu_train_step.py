@@ -163,3 +163,30 @@ def test_graphed_step_matches_eager():
         assert torch.allclose(la, lb, rtol=2e-3), (i, la, lb)
     assert a.step_count == b.step_count == 5 and float(b.step_dev) == 5.0
     assert float((a.P - b.P).abs().max()) <= 1.05e-3          # <= 5 steps x 2 lr: the updates are ~lr * sign(g)
+
+
+def test_eval_after_graph_replays_uses_the_current_weights():
+    """a graph replay updates parameters and BatchNorm running statistics through raw device pointers, so no tensor
+    version moves; the module's eval-mode cache (packed bf16 weights, folded BN) must still be refreshed.  train x3 (eager warm-up,
+    capture + replay, replay) -> eval -> train x2 (replays) -> eval: each eval forward must equal a FRESH UNet loaded from the
+    module's current state_dict, and set_hyperparameters with unchanged values must keep the captured graph."""
+    eng = _engine()
+    noisy, clean = batch(104, (4, 1, 64, 32))
+    noisy, clean = noisy.to(DEV), clean.to(DEV)
+    outs = []
+    for round_ in range(2):
+        for _ in range(3 if round_ == 0 else 2):
+            eng.train_step_graphed(noisy, clean)
+        graph = eng._graph["graph"]
+        eng.set_hyperparameters(lr=eng.lr)                    # unchanged -> no recapture
+        assert eng._graph is not None and eng._graph["graph"] is graph
+        eng.model.eval()
+        y = eng.model(noisy)
+        fresh = UNet().eval()
+        fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in eng.model.state_dict().items()})
+        assert torch.equal(y, fresh(noisy)), f"stale eval cache after graphed steps (round {round_})"
+        outs.append(y.clone())
+        eng.model.train()
+    assert not torch.equal(outs[0], outs[1])
+    eng.set_hyperparameters(lr=eng.lr * 0.5)                  # changed -> the baked-in value forces a recapture
+    assert eng._graph is None

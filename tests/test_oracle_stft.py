@@ -85,3 +85,107 @@ def test_griffin_lim_loop_is_a_projector():
     once = so.istft(mag * ang)
     assert full.shape == (128 * 19,) and full.dtype == np.float64
     assert np.max(np.abs(full - once)) <= 1e-12 * np.max(np.abs(once))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Pinning the unpinned oracle harder: three more implementations that share no code with the oracle
+# (scipy.fft.rfft over a strided frame matrix) or with torch.stft: scipy's ShortTimeFFT class, scipy's legacy
+# signal.stft / istft, and the defining O(N^2) DFT sum written out with a complex exponential matrix.  Plus a LIVE librosa
+# comparison that runs wherever librosa is importable (it is absent from this image: requirements.txt:10 pins 0.10.2.post1).
+def _clip(n=24000, seed=5):
+    return synth.make_clip(seed, "R").astype(np.float64)[:n]
+
+
+def test_against_scipy_shorttimefft():
+    import scipy.signal as ss
+    x = _clip()
+    stf = ss.ShortTimeFFT(so.hann_periodic(512), hop=128, fs=1.0, fft_mode="onesided", mfft=512, scale_to=None, phase_shift=None)
+    t = so.num_frames(len(x), True)
+    ref = stf.stft(x, p0=0, p1=t)                       # slice p is centred on sample p*hop, zero padding outside: librosa center=True
+    d = so.stft(x, center=True)
+    assert ref.shape == d.shape == (257, 188)
+    assert np.max(np.abs(d - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # inverse on an INCONSISTENT spectrogram (magnitude x random phase, what test.py:36-37 inverts): ShortTimeFFT synthesises with
+    # the canonical dual window w / sum_shifts(w^2) = w / 1.5, librosa divides the overlap-add by the running window-sum of
+    # squares -- identical wherever four frames overlap.  ShortTimeFFT.istft expects slices from p_min = -1 on: pad with zeros.
+    rng = np.random.default_rng(3)
+    c = np.abs(d) * np.exp(2j * np.pi * rng.random(d.shape))
+    y = so.istft(c)
+    s_full = np.concatenate([np.zeros((257, -stf.p_min)), c, np.zeros((257, 2))], axis=1)
+    ref_y = stf.istft(s_full, k0=0, k1=128 * (t - 1))
+    assert y.shape == ref_y.shape == (23936,)
+    inner = slice(256, 23936 - 256)
+    assert np.max(np.abs(y[inner] - ref_y[inner])) <= 1e-12 * np.max(np.abs(ref_y))
+
+
+@pytest.mark.parametrize("n", [24000, 16000, 8100])
+def test_against_scipy_legacy_stft(n):
+    import scipy.signal as ss
+    x = _clip(n)
+    w = so.hann_periodic(512)
+    _f, _t, z = ss.stft(x, window=w, nperseg=512, noverlap=384, nfft=512, boundary="zeros", padded=False, return_onesided=True,
+                        scaling="spectrum")
+    ref = z * w.sum()                                   # 'spectrum' scaling divides by sum(w)
+    d = so.stft(x, center=True)
+    assert ref.shape == d.shape
+    assert np.max(np.abs(d - ref)) <= 1e-12 * np.max(np.abs(ref))
+    # legacy istft (its own overlap-add + window-sum normalisation); it returns the full padded-trimmed signal, compare the
+    # hop*(T-1) samples librosa.istft keeps
+    _tt, yr = ss.istft(z, window=w, nperseg=512, noverlap=384, nfft=512, input_onesided=True, boundary=True, scaling="spectrum")
+    y = so.istft(d)
+    assert np.max(np.abs(y - yr[: len(y)])) <= 1e-12 * np.max(np.abs(y))
+
+
+@pytest.mark.parametrize("center", [False, True])
+def test_against_the_defining_dft_sum(center):
+    """D[f, t] = sum_n w[n] x_t[n] exp(-2 pi i f n / 512) evaluated literally, no FFT anywhere."""
+    x = _clip(4000, seed=9)
+    xp = np.pad(x, (256, 256)) if center else x
+    t = 1 + (len(xp) - 512) // 128
+    n = np.arange(512)
+    e = np.exp(-2j * np.pi * np.outer(np.arange(257), n) / 512.0)
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * n / 512)
+    ref = np.stack([e @ (w * xp[128 * i: 128 * i + 512]) for i in range(t)], axis=1)
+    d = so.stft(x, center=center)
+    assert d.shape == ref.shape
+    assert np.max(np.abs(d - ref)) <= 1e-11 * np.max(np.abs(ref))
+    # inverse by the literal sums: y_t[n] = (1/512) sum_k c_k Re(D[k,t] e^{+2 pi i k n/512}) (c2r weights 1,2,...,2,1; Im of DC /
+    # Nyquist ignored), windowed overlap-add, division by the window sum of squares, trim 256 each side
+    if center:
+        c = np.full(257, 2.0); c[0] = c[256] = 1.0
+        dd = d.astype(np.complex128).copy()
+        dd[0] = dd[0].real; dd[256] = dd[256].real
+        frames = ((c[:, None] * dd).T @ np.conj(e)).real / 512.0 * w        # (T, 512)
+        full = 512 + 128 * (t - 1)
+        acc, wss = np.zeros(full), np.zeros(full)
+        for i in range(t):
+            acc[128 * i: 128 * i + 512] += frames[i]
+            wss[128 * i: 128 * i + 512] += w * w
+        ref_y = (acc / np.where(wss > 0, wss, 1.0))[256: full - 256]
+        y = so.istft(d)
+        assert np.max(np.abs(y - ref_y)) <= 1e-11 * np.max(np.abs(ref_y))
+
+
+def test_against_torchaudio_spectrogram():
+    ta = pytest.importorskip("torchaudio")
+    x = _clip()
+    spec = ta.transforms.Spectrogram(n_fft=512, hop_length=128, power=1.0, center=True, pad_mode="constant",
+                                     window_fn=lambda n: torch.hann_window(n, periodic=True, dtype=torch.float64))
+    ref = spec(torch.from_numpy(x)).numpy()
+    m = so.stft_mag(x, True)
+    assert np.max(np.abs(m - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_against_live_librosa():
+    """Runs wherever librosa is installed ("if the B200 box happens to have librosa, add a live comparison; never depend
+    on it").  The calls are the reference's own: create_train_dataset.py:167-173, create_test_dataset.py:39-40, test.py:40."""
+    librosa = pytest.importorskip("librosa")
+    x32 = synth.make_clip(2, "R")
+    for center in (False, True):
+        d = librosa.stft(x32[:16000] if not center else x32, n_fft=512, hop_length=128, center=center)
+        mag, _ = librosa.magphase(d)
+        ours = so.stft(x32[:16000] if not center else x32, center=center)
+        assert ours.dtype == d.dtype and ours.shape == d.shape
+        assert np.max(np.abs(np.abs(ours) - mag)) <= 1e-6 * np.max(mag)
+    d = so.stft(x32.astype(np.float64), center=True)
+    assert np.max(np.abs(so.istft(d) - librosa.istft(d, hop_length=128))) <= 1e-12
