@@ -19,7 +19,8 @@
 // Window / twiddle tables are indexed by warp-uniform values only (broadcast shared-memory loads): no registers are
 // spent on them, so pass 2 can hold two rows (64 registers) per thread.
 #define ADN_PACKED_FP32 1            // packed fp32x2 butterflies (see adn_common.cuh)
-#include "adn_common.cuh"
+#include <cstdlib>
+#include "tc_common.cuh"
 #include "adn_tables.inc"
 
 namespace adn {
@@ -315,6 +316,248 @@ stft_kernel(const float* __restrict__ wave, long long n_clips, int length, long 
     cp_async_wait_all();
 }
 
+
+// ------------------------------------------------------------------------------------------------ warp-specialised variant
+// stft_kernel's two CTAs per SM run the same barrier-separated phases and stall together: after each __syncthreads all 16
+// warps of the SM issue their shared-memory loads at once and nobody has arithmetic to issue until the data arrive (LDS was
+// 26 % / 17 % of the stall samples of pass 1 / pass 2; the kernel issues on 67 % of the cycles although it is issue-bound:
+// a packed fp32x2 instruction occupies the issue port for two cycles, scripts/microbench/issue_mix.cu).
+// stft_ws_kernel removes the CTA-wide barriers.  One CTA of 16 warps per SM: warps 0-7 run pass 1 (window, radix-16 over n1,
+// twiddles -> exchange array), warps 8-15 run pass 2 (radix-16 over n2, real-FFT split, magnitudes, stores), one tile apart,
+// over TWO exchange arrays and THREE sample buffers.  All hand-offs are mbarriers with one arrival per warp, so a warp only
+// ever waits for data it needs: pass-1 warps drift apart (their load bursts meet other warps' butterflies), and the pass-2
+// warps work on tile t while pass 1 already transforms tile t + 1.
+constexpr int WS_THREADS = 512;
+constexpr int WS_SAMPLE_SLOTS = 3;
+constexpr int WS_SMEM_BYTES = WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES + 2 * ST_WORK_BYTES + ST_TABLE_BYTES + 128;
+
+// mbarrier wait for the spectral kernels: try_wait suspends the warp in hardware until the phase flips (or a system time limit
+// passes), so the loop body is as small as possible -- in an issue-bound kernel every polling instruction is taken from a warp that
+// has arithmetic to issue.  Bounded: a barrier that never flips is a protocol bug and traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// (clip, tile-in-clip) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: advanced with adds instead of a division per tile
+struct TileWalk {
+    int clip, tin, dq, dr, tpc;
+    __device__ __forceinline__ void init(int first, int step, int tiles_per_clip) {
+        tpc = tiles_per_clip; clip = first / tpc; tin = first - clip * tpc; dq = step / tpc; dr = step - dq * tpc;
+    }
+    __device__ __forceinline__ void next() {
+        clip += dq; tin += dr;
+        if (tin >= tpc) { tin -= tpc; ++clip; }
+    }
+};
+
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+stft_ws_kernel(const float* __restrict__ wave, long long n_clips, int length, long long clip_stride, int center,
+               int n_frames, int tiles_per_clip, float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* const samples = reinterpret_cast<float*>(smem_raw);                                     // [slot][hop][130]
+    float2* const work0 = reinterpret_cast<float2*>(smem_raw + WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES);   // [buf][k1*16 + n2][frame]
+    float2* const s_hann = reinterpret_cast<float2*>(smem_raw + WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES + 2 * ST_WORK_BYTES);
+    float2* const s_tw256 = s_hann + 256;
+    float2* const s_tw512 = s_hann + 512;
+    const uint32_t bars = smem_u32(smem_raw + WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES + 2 * ST_WORK_BYTES + ST_TABLE_BYTES);
+    // mbarriers (8 bytes each): samples_ready[3] (256 copy arrivals), slot_free[3] (8 warps), full[2] (8), empty[2] (8)
+    const uint32_t bar_ready = bars, bar_free = bars + 24, bar_full = bars + 48, bar_empty = bars + 64;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int role = __shfl_sync(0xffffffffu, tid >> 8, 0);       // 0: pass 1, 1: pass 2
+    const int gt = tid & 255;
+    const int w = __shfl_sync(0xffffffffu, gt >> 5, 0);           // warp index inside the role
+    if (tid < 256) {
+        s_hann[tid] = adn_c_hann512_half[16 * (tid & 15) + (tid >> 4)];      // [n2][n1]
+        s_tw256[tid] = adn_c_tw256[tid >> 4][tid & 15];                      // [n2][k1]
+        s_tw512[tid] = adn_c_tw512[(tid >> 4) + 16 * (tid & 15)];            // [a][k2]: W512^(a + 16 k2)
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(bar_ready + 8 * i, 256); mbar_init(bar_free + 8 * i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, 8); mbar_init(bar_empty + 8 * i, 8); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    const int total_tiles = (int)n_clips * tiles_per_clip;        // < 2^31 (host check)
+    const int pad = center ? ADN_N_FFT / 2 : 0;
+    const int n_local = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;      // tiles of this CTA (>= 1)
+
+    if (role == 0) {
+        // =========================================================== pass-1 warps
+        TileWalk st;                                              // the tile being STAGED (two ahead of the one being transformed)
+        st.init((int)blockIdx.x, (int)gridDim.x, tiles_per_clip);
+        int st_slot = 0;
+        auto stage = [&]() {                                      // samples of the next tile -> slot st_slot, completion on bar_ready
+            const int t0 = st.tin * TF;
+            const int nf = min(TF, n_frames - t0);
+            stft_stage(samples + st_slot * (ST_SAMPLES_BYTES / 4), wave + st.clip * clip_stride, out, t0 * ADN_HOP - pad, length, nf + 3, gt);
+            cp_async_mbar_arrive_noinc(bar_ready + 8 * st_slot);
+            st.next();
+            st_slot = st_slot == WS_SAMPLE_SLOTS - 1 ? 0 : st_slot + 1;
+        };
+        if (0 < n_local) stage();
+        if (1 < n_local) stage();
+        int slot = 0;                                             // sample slot of tile i = i % 3
+        uint32_t ready_par = 0;                                   // parity of bar_ready[slot] for tile i: (i / 3) & 1
+        uint32_t free_bits = 0;                                   // bit s: parity of the NEXT wait on bar_free[s]
+        for (int i = 0; i < n_local; ++i) {
+            const int buf = i & 1;
+            mbar_wait_sleep(bar_ready + 8 * slot, ready_par);
+            const float* fr = samples + slot * (ST_SAMPLES_BYTES / 4) + lane * ST_ROW_STRIDE;
+            float2 v0[16], v1[16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n2 = w + 8 * c;
+                const float4* hw = reinterpret_cast<const float4*>(s_hann + n2 * 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 hq = hw[j];
+                    const float2 s0 = *reinterpret_cast<const float2*>(fr + ((2 * j) >> 2) * ST_ROW_STRIDE + 32 * ((2 * j) & 3) + 2 * n2);
+                    const float2 s1 = *reinterpret_cast<const float2*>(fr + ((2 * j + 1) >> 2) * ST_ROW_STRIDE + 32 * ((2 * j + 1) & 3) + 2 * n2);
+                    (c ? v1 : v0)[2 * j] = pk_mul(s0, make_float2(hq.x, hq.y));
+                    (c ? v1 : v0)[2 * j + 1] = pk_mul(s1, make_float2(hq.z, hq.w));
+                }
+            }
+            // this warp is done with the sample slot (the multiplies above consumed every load)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_free + 8 * slot);
+            // refill: tile i + 2 goes into the slot tile i - 1 used (= st_slot); wait until all eight warps have released it
+            if (i + 2 < n_local) {
+                if (i >= 1) {
+                    mbar_wait_sleep(bar_free + 8 * st_slot, (free_bits >> st_slot) & 1u);
+                    free_bits ^= 1u << st_slot;
+                }
+                stage();
+            }
+            if (slot == WS_SAMPLE_SLOTS - 1) { slot = 0; ready_par ^= 1u; } else ++slot;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n2 = w + 8 * c;
+                const float4* tq = reinterpret_cast<const float4*>(s_tw256 + n2 * 16);
+                float2 tw[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t4 = tq[j];
+                    tw[2 * j] = make_float2(t4.x, t4.y); tw[2 * j + 1] = make_float2(t4.z, t4.w);
+                }
+                if (c == 0) {
+                    dft16<false>(v0);
+#pragma unroll
+                    for (int k1 = 1; k1 < 16; ++k1) v0[k1] = cmul(v0[k1], tw[k1]);
+                } else {
+                    dft16<false>(v1);
+#pragma unroll
+                    for (int k1 = 1; k1 < 16; ++k1) v1[k1] = cmul(v1[k1], tw[k1]);
+                }
+            }
+            // exchange array `buf` was last read by pass 2 of tile i - 2
+            if (i >= 2) mbar_wait_sleep(bar_empty + 8 * buf, ((i - 2) >> 1) & 1);
+            float2* const work = work0 + buf * (ST_WORK_BYTES / 8);
+#pragma unroll
+            for (int k1 = 0; k1 < 16; ++k1) {
+                work[(k1 * 16 + w) * TF + lane] = v0[k1];
+                work[(k1 * 16 + w + 8) * TF + lane] = v1[k1];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * buf);       // release: the warp's stores are ordered before the arrival
+        }
+        cp_async_wait_all();
+    } else {
+        // =========================================================== pass-2 warps
+        const int a = w, b = (w == 0) ? 8 : 16 - w;
+        TileWalk tw_;
+        tw_.init((int)blockIdx.x, (int)gridDim.x, tiles_per_clip);
+        for (int i = 0; i < n_local; ++i, tw_.next()) {
+            const int buf = i & 1;
+            const int cur_clip = tw_.clip, cur_t0 = tw_.tin * TF;
+            const int nf = min(TF, n_frames - cur_t0);
+            mbar_wait_sleep(bar_full + 8 * buf, (i >> 1) & 1);
+            const float2* const work = work0 + buf * (ST_WORK_BYTES / 8);
+            float2 A[16], B[16];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) A[n2] = work[(a * 16 + n2) * TF + lane];
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) B[n2] = work[(b * 16 + n2) * TF + lane];
+            dft16<false>(A);                                         // A[k2] = Z[a + 16 k2]
+            dft16<false>(B);                                         // B[k2] = Z[b + 16 k2]
+            __syncwarp();                                            // both rows are consumed: pass 1 may overwrite the array
+            if (lane == 0) mbar_arrive(bar_empty + 8 * buf);
+            auto split = [&](float2 tw, float2& zk, float2& zp) {                        // tw = W512^k
+                const float2 e = pk_add(zk, make_float2(zp.x, -zp.y));                    // Zk + conj(Zp)
+                const float2 o = pk_add(rot_mi(zk), make_float2(zp.y, zp.x));             // -i (Zk - conj(Zp))
+                const float2 wo = cmul(o, tw);
+                zk = cadd(e, wo);
+                zp = csub(e, wo);
+            };
+            auto mag = [](float2 z) { return sqrt_approx(fmaf(z.x, z.x, z.y * z.y)); };
+            const bool live = lane < nf;
+            const long long row0 = ((long long)cur_clip * ADN_N_BINS) * n_frames + cur_t0 + lane;
+            const long long step = 16LL * n_frames;
+            const float4* twa = reinterpret_cast<const float4*>(s_tw512 + a * 16);        // W512^(a + 16 k2), two per load
+            if (w != 0) {
+                float* pa = out + row0 + (long long)a * n_frames;                         // rows a + 16 k2, upwards
+                float* pb = out + row0 + (long long)(b + 240) * n_frames;                 // rows b + 16 k2, downwards from k2 = 15
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {                                             // 256 - k = b + 16 (15 - k2)
+                    const float4 t4 = twa[j];
+                    split(make_float2(t4.x, t4.y), A[2 * j], B[15 - 2 * j]);
+                    split(make_float2(t4.z, t4.w), A[2 * j + 1], B[14 - 2 * j]);
+                    const float m0 = mag(A[2 * j]), m1 = mag(B[15 - 2 * j]), m2 = mag(A[2 * j + 1]), m3 = mag(B[14 - 2 * j]);
+                    if (live) {
+                        __stcs(pa, m0);
+                        __stcs(pb, m1);
+                        __stcs(pa + step, m2);
+                        __stcs(pb - step, m3);
+                    }
+                    pa += 2 * step;
+                    pb -= 2 * step;
+                }
+            } else {
+                const float4* twb = reinterpret_cast<const float4*>(s_tw512 + 8 * 16);    // W512^(8 + 16 k2)
+                const float x0 = fabsf(2.f * (A[0].x + A[0].y)), x256 = fabsf(2.f * (A[0].x - A[0].y));     // bins 0 and 256 are real
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t4 = twa[j];                                             // a = 0: W512^(16 k2)
+                    if (j > 0) split(make_float2(t4.x, t4.y), A[2 * j], A[16 - 2 * j]);
+                    split(make_float2(t4.z, t4.w), A[2 * j + 1], A[15 - 2 * j]);
+                }
+                A[8] = make_float2(2.f * A[8].x, -2.f * A[8].y);     // k = 128 pairs with itself: X[128] = 2 conj(Z[128])
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t4 = twb[j];
+                    split(make_float2(t4.x, t4.y), B[2 * j], B[15 - 2 * j]);
+                    split(make_float2(t4.z, t4.w), B[2 * j + 1], B[14 - 2 * j]);
+                }
+                if (live) {
+                    float* p0 = out + row0;                                               // rows 16 k2 (A) and 8 + 16 k2 (B)
+                    __stcs(p0, x0);
+                    __stcs(p0 + 16 * step, x256);
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        if (k2 > 0) __stcs(p0 + k2 * step, mag(A[k2]));
+                        __stcs(p0 + 8LL * n_frames + k2 * step, mag(B[k2]));
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <bool COMPLEX_OUT, bool CROP>
 static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64_t clip_stride, int center, float* out,
                        float* crop, int f_out, int t_out, cudaStream_t stream) {
@@ -334,6 +577,16 @@ static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64
     if (total >= ((int64_t)1 << 31) - 4096) return ADN_ERR_ARG;
     if (CROP && (T < t_out || ADN_N_BINS < f_out))                         // zero padding of data_loader.py:54-72
         ADN_CUDA_TRY(cudaMemsetAsync(crop, 0, (size_t)n_clips * f_out * t_out * sizeof(float), stream));
+    static const int impl = getenv("ADN_STFT_IMPL") ? atoi(getenv("ADN_STFT_IMPL")) : 2;        // 1: barrier-phased CTAs, 2: warp-specialised
+    if (impl == 2 && !COMPLEX_OUT && !CROP) {
+        static unsigned char smem_set[64] = {0};
+        ADN_CUDA_TRY(ensure_dyn_smem(stft_ws_kernel, WS_SMEM_BYTES, smem_set));
+        const long long sms = num_sms();
+        const int grid = (int)(total < sms ? total : sms);          // persistent: one 16-warp CTA per SM
+        stft_ws_kernel<<<grid, WS_THREADS, WS_SMEM_BYTES, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, tiles_per_clip, out);
+        ADN_LAUNCH_CHECK();
+        return ADN_OK;
+    }
     const size_t smem = ST_SMEM_BYTES;
     auto kern = stft_kernel<COMPLEX_OUT, CROP>;
     static unsigned char smem_set[64] = {0};

@@ -94,9 +94,11 @@ def test_stft_second_output_is_the_loader_transform(length, center):
     mag = spectral.stft_mag_batched(x, center)
     crop, mag2 = spectral.stft_mag_train_batched(x, center, with_mag=True)
     only = spectral.stft_mag_train_batched(x, center)
-    assert torch.equal(mag2, mag)
+    # the plain |STFT| entry may run another kernel variant than the fused one (ptxas contracts packed mul + add pairs differently
+    # per kernel: last-bit differences), so the transform is checked against the fused kernel's OWN magnitudes
+    assert torch.allclose(mag2, mag, rtol=0.0, atol=2e-6 * float(mag.abs().max()))
     ref = np.zeros((3, 1, 256, 64), np.float32)
-    m = mag.cpu().numpy().astype(np.float16).astype(np.float32)
+    m = mag2.cpu().numpy().astype(np.float16).astype(np.float32)
     f, t = min(256, m.shape[1]), min(64, m.shape[2])
     ref[:, 0, :f, :t] = m[:, :f, :t]
     assert crop.shape == (3, 1, 256, 64)
