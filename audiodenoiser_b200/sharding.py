@@ -10,6 +10,7 @@ which lets the host logic be tested with the gloo backend on CPU (tests/test_sha
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -72,6 +73,75 @@ def all_gather_rows(local: torch.Tensor, n_total: int, group=None, out: torch.Te
     return out[:n_total]
 
 
+class PeerGather:
+    """All-gather of the row-sharded audio over NVLink by the COPY ENGINES instead of ncclAllGather.
+
+    Why: the hot path's kernels are persistent (one CTA per SM, tiles assigned statically); an NCCL kernel that holds even a
+    few SMs while they run delays the CTAs that land on those SMs by a whole kernel (round 1: 1 -> 8 GPUs lost 5 %, most of it
+    here).  A peer copy needs no SM.  Every rank owns a symmetric (world * per, ...) buffer (torch symmetric memory: cuMem
+    allocations mapped into every peer over NVLink / NVSwitch); a step copies the local shard into slot `rank` of EVERY rank's
+    buffer with cudaMemcpyAsync on a side stream, then joins a device-side barrier of the group on the same stream.  After the
+    barrier the local buffer holds all shards in rank (= clip) order.  Two buffers alternate, so the gather of step i overlaps the
+    kernels of step i + 1.  `available()` is False without CUDA symmetric memory (then the caller uses NCCL)."""
+
+    def __init__(self, per: int, tail: tuple, dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = _world(group)
+        self.per, self.tail = int(per), tuple(tail)
+        grp = group if group is not None else dist.group.WORLD
+        self.stream = torch.cuda.Stream(device)
+        self.bufs, self.handles, self.peers = [], [], []
+        for _ in range(2):
+            buf = symm.empty((self.world * self.per,) + self.tail, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, grp)
+            self.bufs.append(buf)
+            self.handles.append(hdl)
+            self.peers.append([hdl.get_buffer(r, tuple(buf.shape), dtype) for r in range(self.world)])
+        self.turn = 0
+        self.pending = [None, None]
+
+    @staticmethod
+    def available(device) -> bool:
+        try:
+            import torch.distributed._symmetric_memory as symm  # noqa: F401
+        except Exception:  # noqa: BLE001
+            return False
+        return torch.device(device).type == "cuda" and dist.is_initialized() and dist.get_backend() == "nccl"
+
+    def start(self, local: torch.Tensor, n_total: int):
+        """Begin gathering `local` (n_r rows) of this step; returns the (n_total, ...) view of the buffer it lands in (complete
+        after `finish()`, or once the event of this turn has been waited on)."""
+        b = self.turn
+        self.turn ^= 1
+        comp = torch.cuda.current_stream(local.device)
+        if self.pending[b] is not None:                        # the gather that last used this buffer (two steps ago)
+            comp.wait_event(self.pending[b])
+        lo = self.rank * self.per
+        own = self.bufs[b][lo:lo + local.shape[0]]
+        own.copy_(local, non_blocking=True)                    # own slot first, on the compute stream: `local` may be reused at once
+        ready = torch.cuda.Event()
+        ready.record(comp)
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            for r in range(1, self.world):                     # ring order: at any moment every rank receives from one peer
+                peer = (self.rank + r) % self.world
+                self.peers[b][peer][lo:lo + local.shape[0]].copy_(own, non_blocking=True)
+            # device-side barrier of the group on this stream: when it completes here, every rank's copies into THIS rank's buffer
+            # have landed.  It also orders the steps across ranks: nobody can start step i + 2 (same buffer) before all finished step i.
+            self.handles[b].barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.pending[b] = done
+        return self.bufs[b][:n_total]
+
+    def finish(self):
+        comp = torch.cuda.current_stream()
+        for i, ev in enumerate(self.pending):
+            if ev is not None:
+                comp.wait_event(ev)
+                self.pending[i] = None
+
+
 def all_reduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     """In-place all-reduce(SUM) of a small float64 vector of partial sums / counts."""
     world, _ = _world(group)
@@ -113,17 +183,29 @@ class ShardedDenoiser:
         self._gather_work = [None, None]
         self._gather_turn = 0
         self._sums = None
+        self._sums_bufs = None
+        self._sums_turn = 0
+        self._sums_work = [None, None]
+        self._peer = None                 # PeerGather (copy-engine all-gather), created on first use when available
+        self._peer_failed = False
+        self.gather_impl = "none"
 
     def local_range(self, n_total: int) -> tuple[int, int]:
         return shard_range(n_total, self.world, self.rank)
 
     def error_sums(self, pred_mag: torch.Tensor, target_mag: torch.Tensor) -> torch.Tensor:
-        """Device float64 [sum|d|, sum t^2, sum d^2, count] of this rank's shard (CUDA kernel adn_spec_error_sums_f64)."""
+        """Device float64 [sum|d|, sum t^2, sum d^2, count] of this rank's shard (CUDA kernel adn_spec_error_sums_f64).  Two
+        result buffers alternate, so the asynchronous all-reduce of one step never meets the next step's writes."""
         from . import _lib
         if not pred_mag.is_cuda:
             raise _lib.AdnError("error_sums needs CUDA tensors (no CPU fallback)")
-        if self._sums is None or self._sums.device != pred_mag.device:
-            self._sums = torch.zeros(8, dtype=torch.float64, device=pred_mag.device)
+        if self._sums_bufs is None or self._sums_bufs[0].device != pred_mag.device:
+            self._sums_bufs = [torch.zeros(8, dtype=torch.float64, device=pred_mag.device) for _ in range(2)]
+        self._sums_turn ^= 1
+        if self._sums_work[self._sums_turn] is not None:      # the all-reduce that last used this buffer (two steps ago)
+            self._sums_work[self._sums_turn].wait()
+            self._sums_work[self._sums_turn] = None
+        self._sums = self._sums_bufs[self._sums_turn]
         self._sums.zero_()
         p = pred_mag.float().contiguous(); t = target_mag.float().contiguous()
         if p.shape != t.shape:
@@ -143,13 +225,19 @@ class ShardedDenoiser:
 
     def finish(self):
         """Wait for the all-gathers started by ``step(..., overlap_gather=True)``."""
+        if self._peer is not None:
+            self._peer.finish()
+        for i, w in enumerate(self._sums_work):
+            if w is not None:
+                w.wait()
+                self._sums_work[i] = None
         for i, w in enumerate(self._gather_work):
             if w is not None:
                 w.wait()
                 self._gather_work[i] = None
 
     def step(self, wave_local: torch.Tensor, n_total: int, target_mag_local: torch.Tensor | None = None, gather: bool = True,
-             overlap_gather: bool = False):
+             overlap_gather: bool = False, reduce: bool = True):
         """Denoise this rank's clips; returns (audio, sums): ``audio`` is the gathered (n_total, samples) tensor when
         ``gather`` (every rank gets it, rank order = clip order) else the local shard; ``sums`` is the group-reduced
         float64 statistics vector (None without a target).
@@ -159,11 +247,33 @@ class ShardedDenoiser:
         complete once the step after next has been issued, or after ``finish()``."""
         if target_mag_local is not None:
             audio, _mag, den = self.denoiser.denoise(wave_local, return_spectrograms=True)
-            sums = all_reduce_sums(self.error_sums(den, target_mag_local), self.group)
+            sums = self.error_sums(den, target_mag_local)
+            if not reduce:
+                pass                                            # local partial sums only (bench: the no-communication reference run)
+            elif self.world > 1 and overlap_gather and sums.is_cuda:
+                # statistics: NCCL all-reduce started asynchronously (it runs on NCCL's stream); `sums` is final after finish()
+                self._sums_work[self._sums_turn] = dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            else:
+                sums = all_reduce_sums(sums, self.group)
         else:
             audio, sums = self.denoiser.denoise(wave_local), None
-        if gather and self.world > 1 and overlap_gather:
+        if gather and self.world > 1 and overlap_gather and not self._peer_failed and audio.is_cuda and os.environ.get("ADN_GATHER", "peer") != "nccl":
             per = -(-n_total // self.world)
+            if self._peer is None and PeerGather.available(audio.device):
+                try:
+                    self._peer = PeerGather(per, tuple(audio.shape[1:]), audio.dtype, audio.device, self.group)
+                    self.gather_impl = "copy-engine peer copies into symmetric buffers (no SM), device barrier per step"
+                except Exception as exc:  # noqa: BLE001  (no symmetric memory on this box / torch build: use NCCL)
+                    self._peer_failed = True
+                    self.gather_impl = f"ncclAllGather (symmetric memory unavailable: {type(exc).__name__})"
+            elif self._peer is None:
+                self._peer_failed = True
+        if gather and self.world > 1 and overlap_gather and self._peer is not None:
+            audio = self._peer.start(audio, n_total)
+        elif gather and self.world > 1 and overlap_gather:
+            per = -(-n_total // self.world)
+            if self.gather_impl == "none":
+                self.gather_impl = "ncclAllGather on NCCL's stream"
             shape = (self.world * per,) + tuple(audio.shape[1:])
             b = self._gather_turn
             self._gather_turn ^= 1

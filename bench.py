@@ -321,6 +321,14 @@ def run_b200(args):
     launches0 = net.launch_count
     ms_dev = timed(step_device, args.steps, args.warmup, sampler)
     clocks = sampler.summary()
+    comm = None
+    if world > 1:
+        # the same steps with NO communication (no gather, local statistics only): the difference is what the collectives cost
+        ms_nocomm = timed(lambda i: job.step(dev_batches[i % rot], n_total, clean_mags[i % rot], gather=False, reduce=False),
+                          args.steps, args.warmup, ClockSampler(local_rank))
+        comm = {"gather": job.gather_impl, "statistics": "ncclAllReduce of 8 float64, asynchronous",
+                "ms_per_step_without_communication": ms_nocomm / args.steps,
+                "comm_exposed_ms": (ms_dev - ms_nocomm) / args.steps}
     run_host(0, args.warmup)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -471,7 +479,8 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {**workload_config(args, t_frames, batch),
                        "l2": f"inputs rotate over {rot} resident batches; every step rewrites ~{unet_workspace_gb(batch, 257, t_frames):.1f} GB of activations (>> 126 MB L2)",
-                       "collectives": "all_gather(audio, overlapped with the next step's kernels) + all_reduce(error sums) per step" if n_gpus > 1 else "none (single GPU)"},
+                       "collectives": (f"all-gather of the audio ({job.gather_impl}), overlapped with the next step's kernels + asynchronous all_reduce(error sums) per step"
+                                       if n_gpus > 1 else "none (single GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(batch * length * 4) * n_gpus, "d2h_bytes_per_step": int(batch * n_out * 4 + 32) * n_gpus},
             "gpu_launches": int(launches_per_step * args.steps),
@@ -485,6 +494,7 @@ def run_b200(args):
             "cpu_baseline": cpu_baseline,
             "parity": parity,
             "gather_check": gather_check,
+            "communication": comm,
             "train_step": train,
         }
         emit(line)
