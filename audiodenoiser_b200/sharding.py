@@ -308,3 +308,29 @@ def average_gradients_(flat_grad, group=None):
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
         flat_grad.div_(world)
     return flat_grad
+
+
+class _GradBucket:
+    """One asynchronous all-reduce(AVG) over a slice of the flat gradient buffer (see TrainEngine.backward)."""
+
+    def __init__(self, flat_slice, group):
+        self.t, self.world, self.work = flat_slice, 1, None
+        if dist.is_available() and dist.is_initialized():
+            self.world = dist.get_world_size(group)
+        if self.world > 1 and flat_slice.numel() > 0:
+            op = dist.ReduceOp.AVG if flat_slice.is_cuda else dist.ReduceOp.SUM
+            self.work = dist.all_reduce(flat_slice, op=op, group=group, async_op=True)
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+            if not self.t.is_cuda:
+                self.t.div_(self.world)
+            self.work = None
+
+
+def average_gradients_async(flat_slice, group=None) -> _GradBucket:
+    """Start averaging one BUCKET of the flat gradient buffer over the ranks and return a handle (``.wait()``): the training engine
+    launches a bucket as soon as the backward pass has produced its last gradient, so the collective runs on NCCL's stream
+    under the remaining backward kernels (torch DDP's bucketed overlap)."""
+    return _GradBucket(flat_slice, group)

@@ -80,6 +80,7 @@ class TrainEngine:
                 view.copy_(params[key].detach().to(dev, torch.float32))
                 params[key].data = view                      # the module's parameters now alias the flat buffer
         self.buffers = dict(self.model.named_buffers())
+        self._nbt = [b for k, b in self.buffers.items() if k.endswith("num_batches_tracked")]
         self.ones = torch.ones(1024, dtype=torch.float32, device=dev)
         self.zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.ws = torch.empty(int(self.lib.adn_train_workspace_bytes()), dtype=torch.uint8, device=dev)
@@ -87,6 +88,8 @@ class TrainEngine:
         self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # AdamW step count, advanced on the device
         self._graph = None
+        self._bucketed = False            # backward() launches the DDP gradient buckets (set by train_step only)
+        self._buckets = []
         self.mel_fb = mel_filterbank().to(dev)
         self.loss_out = torch.empty(4, dtype=torch.float32, device=dev)
         self._loss_ws = None
@@ -224,10 +227,9 @@ class TrainEngine:
                                                   self.buffers[f"{bn}.running_mean"].data_ptr(), self.buffers[f"{bn}.running_var"].data_ptr(),
                                                   scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), self.ws.data_ptr(), s),
                        f"bn stats {bn}")
-            self.buffers[f"{bn}.num_batches_tracked"].add_(1)
             y = torch.empty_like(z)
             _lib.check(lib.adn_bn_relu_apply_bf16(z.data_ptr(), scale.data_ptr(), shift.data_ptr(), pixels, co, y.data_ptr(), s), f"bn apply {bn}")
-            self.launch_count += 5
+            self.launch_count += 4
             sv[(p, ci_)] = (z, y, src0, src1)
             return y
 
@@ -259,6 +261,8 @@ class TrainEngine:
             _lib.check(lib.adn_head1x1_forward_f32(cur.data_ptr(), self._pptr("out.weight"), self._pptr("out.bias"), n * h * w, out.data_ptr(), s), "head")
             self.launch_count += 1
             sv["head_in"] = cur
+            torch._foreach_add_(self._nbt, 1)                # the 18 num_batches_tracked counters of nn.BatchNorm2d, one launch
+            self.launch_count += 1
         self.saved = sv
         return out
 
@@ -285,7 +289,7 @@ class TrainEngine:
             _lib.check(lib.adn_bn_relu_backward_bf16(dy_ptr, dy_ld, z.data_ptr(), pixels, co, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
                                                      invstd.data_ptr(), self._gptr(f"{bn}.weight"), self._gptr(f"{bn}.bias"), dz.data_ptr(), wsp, s),
                        f"bn bwd {bn}")
-            self.launch_count += 4
+            self.launch_count += 3
             wkey = f"{p}.double_conv.{ci_}.weight"
             if c0 + c1 == 1:
                 _lib.check(lib.adn_conv3x3_c1_wgrad_f32(dz.data_ptr(), sv["x"].data_ptr(), n, hh, ww, self._gptr(wkey), wsp, s), "c1 wgrad")
@@ -335,9 +339,13 @@ class TrainEngine:
                                                        d_src.data_ptr(), s), "convT dgrad")
                 self.launch_count += 4
                 cur_dy, cur_ld = d_src, ci
+            # DDP: the decoder's gradients (flat slice from upconv1.up.weight to the end, 39 % of the parameters) are final: their
+            # all-reduce runs under the bottleneck / encoder backward
+            self._start_bucket(self.offsets["upconv1.up.weight"][0], self.numel)
             # bottleneck
             d_a = conv_bwd(layers[9], cur_dy.data_ptr(), cur_ld)
             d_pool = conv_bwd(layers[8], d_a.data_ptr(), 1024)
+            self._start_bucket(self.offsets["bottleneck.double_conv.0.weight"][0], self.offsets["upconv1.up.weight"][0])   # 46 %
             # encoder, levels 3..0
             for l in (3, 2, 1, 0):
                 c = _CH[l]
@@ -348,6 +356,7 @@ class TrainEngine:
                 self.launch_count += 1
                 d_a = conv_bwd(layers[2 * l + 1], dy_s.data_ptr(), c)
                 d_pool = conv_bwd(layers[2 * l], d_a.data_ptr(), c, need_dx=(l > 0))
+            self._start_bucket(0, self.offsets["bottleneck.double_conv.0.weight"][0])                                    # 15 %
         self.saved = None
 
     # ------------------------------------------------------------------ loss (loss.py:83-95)
@@ -372,8 +381,23 @@ class TrainEngine:
     def zero_grad(self):
         self.G.zero_()
 
+    def _start_bucket(self, lo: int, hi: int):
+        """DDP: start the asynchronous all-reduce(AVG) of G[lo:hi] (three buckets per step, launched from backward() in the order
+        the gradients become final: decoder, bottleneck, encoder).  No-op without an initialised process group or in an
+        autograd-driven backward (torch's own DDP wrapper / the reference loop average there)."""
+        if not self._bucketed:
+            return
+        from .sharding import average_gradients_async
+        self._buckets.append(average_gradients_async(self.G[lo:hi], self.group))
+
     def all_reduce_grads(self):
-        """DDP gradient averaging: one NCCL all-reduce over the flat buffer (31.04 M fp32 = 124 MB)."""
+        """DDP gradient averaging (31.04 M fp32 = 124 MB): wait for the buckets backward() launched, or -- when the step did not go
+        through train_step -- one all-reduce over the whole flat buffer."""
+        if self._buckets:
+            for b in self._buckets:
+                b.wait()
+            self._buckets = []
+            return
         from .sharding import average_gradients_
         average_gradients_(self.G, self.group)
 
@@ -395,7 +419,11 @@ class TrainEngine:
         self.zero_grad()
         out = self.forward(noisy)
         losses, d_pred = self.loss_and_grad(out, clean)
-        self.backward(d_pred)
+        self._bucketed = True
+        try:
+            self.backward(d_pred)
+        finally:
+            self._bucketed = False
         self.all_reduce_grads()
         self.optimizer_step()
         return losses

@@ -462,6 +462,7 @@ def run_b200(args):
                         "sample": f"{len(waves)} clip(s) of the same batch, variant {args.variant}: float64 numpy/scipy STFT -> fp32 torch-CPU "
                                   f"UNet -> {GL_ITERATIONS}-iteration istft/stft loop + istft; {dt:.2f} s"}
 
+    gather_impl = job.gather_impl
     train = None
     if args.train_steps > 0:
         del den, job, eager
@@ -479,7 +480,7 @@ def run_b200(args):
             "dtype": "bf16", "data": "synthetic",
             "config": {**workload_config(args, t_frames, batch),
                        "l2": f"inputs rotate over {rot} resident batches; every step rewrites ~{unet_workspace_gb(batch, 257, t_frames):.1f} GB of activations (>> 126 MB L2)",
-                       "collectives": (f"all-gather of the audio ({job.gather_impl}), overlapped with the next step's kernels + asynchronous all_reduce(error sums) per step"
+                       "collectives": (f"all-gather of the audio ({gather_impl}), overlapped with the next step's kernels + asynchronous all_reduce(error sums) per step"
                                        if n_gpus > 1 else "none (single GPU)")},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(batch * length * 4) * n_gpus, "d2h_bytes_per_step": int(batch * n_out * 4 + 32) * n_gpus},
@@ -606,7 +607,7 @@ def run_train_bench(args, dev, world, rank, barrier, max_over_ranks, batch_overr
            "ms_per_step": ms_dev, "pairs_per_s": b * world / (ms_dev * 1e-3), "e2e_ms_per_step": ms_e2e,
            "e2e_pairs_per_s": b * world / (ms_e2e * 1e-3), "tflops": flops / (ms_dev * 1e-3) / 1e12, "kernel_launches_per_step": launches, "cuda_graph": True,
            "h2d_bytes_per_step": 2 * b * 256 * 64 * 4 * world, "d2h_bytes_per_step": 16 * world,
-           "losses_after_warmup": losses, "parallelism": f"ddp{world}: one all_reduce(AVG) of the flat fp32 gradient (31.04 M elements) per step" if world > 1 else "single GPU"}
+           "losses_after_warmup": losses, "parallelism": f"ddp{world}: all_reduce(AVG) of the flat fp32 gradient (31.04 M elements) in three buckets launched from backward (decoder 39 %, bottleneck 46 %, encoder 15 %), NCCL stream under the remaining backward kernels" if world > 1 else "single GPU"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and batch_override is None:
         from oracle.train_oracle import TrainOracle
         torch.set_num_threads(os.cpu_count() or 1)

@@ -35,7 +35,14 @@ def _worker(rank, world, port, q):
         noisy, clean = batch(201, (4, 1, 32, 32))
         lo, hi = sharding.shard_range(4, world, rank)
         g = _flat_grads(noisy[lo:hi], clean[lo:hi])
+        g2 = g.clone()
         sharding.average_gradients_(g)
+        # the bucketed, asynchronous form TrainEngine.backward uses (three slices launched as they become final, waited later)
+        cuts = [0, g2.numel() // 7, g2.numel() // 2, g2.numel()]
+        handles = [sharding.average_gradients_async(g2[cuts[i]:cuts[i + 1]]) for i in (2, 1, 0)]
+        for h in handles:
+            h.wait()
+        assert torch.equal(g2, g), "bucketed average differs from the single all-reduce"
         q.put((rank, g[::997].tolist()))           # plain floats: a tensor in a Queue needs the sender alive at receive time
     finally:
         dist.destroy_process_group()
