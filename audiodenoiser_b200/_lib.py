@@ -30,6 +30,8 @@ SIGNATURES = {
     "adn_stft_mag_crop_f16_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P, c_int, c_int, P]),
     "adn_stft_complex_f32": (c_int, [P, c_int64, c_int64, c_int64, c_int, P, P]),
     "adn_istft_ola_f32": (c_int, [P, P, c_int, c_uint64, c_int64, c_int64, P, P]),
+    "adn_istft_ola_counter_f32": (c_int, [P, c_uint64, P, c_int64, c_int64, P, P]),
+    "adn_u64_add": (c_int, [P, c_uint64, P]),
     "adn_random_phasor_c64": (c_int, [c_uint64, c_int64, c_int64, P, P]),
     "adn_stft_mag_host_f32": (c_int, [P, c_int64, c_int64, c_int, P]),
     "adn_istft_ola_host_f32": (c_int, [P, P, c_uint64, c_int64, c_int64, P]),

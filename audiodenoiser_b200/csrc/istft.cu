@@ -62,7 +62,11 @@ __device__ __forceinline__ const T* is_row_ptr(const T* base, int stride_bytes, 
 template <int MODE>
 __global__ void __launch_bounds__(IS_THREADS, 2)
 istft_kernel(const float* __restrict__ mag, const float2* __restrict__ ph, unsigned long long seed,
-             long long n_clips, int n_frames, int tiles_per_clip, float* __restrict__ audio) {
+             const unsigned long long* __restrict__ seed_counter, long long n_clips, int n_frames, int tiles_per_clip,
+             float* __restrict__ audio) {
+    // a device-side call counter added to the seed: a CUDA-graph replay bakes `seed` in, the counter (advanced by
+    // adn_u64_add inside the same graph) still gives every replay a fresh phase, as test.py:36 draws one per call
+    if (MODE == 2 && seed_counter != nullptr) seed += *seed_counter;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* const work = reinterpret_cast<float2*>(smem_raw);            // [o1*16 + i2][frame]
     float* const ybuf = reinterpret_cast<float*>(smem_raw);              // [frame][514], aliases `work`
@@ -274,8 +278,10 @@ __global__ void random_phasor_kernel(unsigned long long seed, long long n_clips,
     }
 }
 
-static int launch_istft(const float* mag, const float* phasor, int spec_is_complex, uint64_t seed, int64_t n_clips,
-                        int64_t n_frames, float* audio, cudaStream_t stream) {
+__global__ void u64_add_kernel(unsigned long long* counter, unsigned long long inc) { *counter += inc; }
+
+static int launch_istft(const float* mag, const float* phasor, int spec_is_complex, uint64_t seed, const uint64_t* seed_counter,
+                        int64_t n_clips, int64_t n_frames, float* audio, cudaStream_t stream) {
     if (n_clips < 0 || n_frames < 1 || n_frames * ADN_N_BINS >= ((int64_t)1 << 31) / 2) return ADN_ERR_ARG;   // 32-bit per-clip byte offsets
     if (n_clips == 0 || n_frames == 1) return ADN_OK;          // hop*(T-1) = 0 samples
     if (!audio) return ADN_ERR_ARG;
@@ -295,8 +301,9 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
     do {                                                                                                           \
         static unsigned char smem_set[64] = {0};                                                                   \
         ADN_CUDA_TRY(ensure_dyn_smem(istft_kernel<MODE>, (int)smem, smem_set));                                    \
-        istft_kernel<MODE><<<grid, IS_THREADS, smem, stream>>>(mag, ph, (unsigned long long)seed, n_clips, (int)n_frames, \
-                                                               tiles_per_clip, audio);                             \
+        istft_kernel<MODE><<<grid, IS_THREADS, smem, stream>>>(mag, ph, (unsigned long long)seed,                  \
+                                                               reinterpret_cast<const unsigned long long*>(seed_counter), n_clips,  \
+                                                               (int)n_frames, tiles_per_clip, audio);              \
     } while (0)
     if (spec_is_complex == 2) ADN_ISTFT_LAUNCH(3);
     else if (spec_is_complex) ADN_ISTFT_LAUNCH(1);
@@ -311,7 +318,22 @@ static int launch_istft(const float* mag, const float* phasor, int spec_is_compl
 
 extern "C" int adn_istft_ola_f32(const float* mag, const float* phasor_c64, int spec_is_complex, uint64_t seed,
                                  int64_t n_clips, int64_t n_frames, float* audio, void* stream) {
-    return adn::launch_istft(mag, phasor_c64, spec_is_complex, seed, n_clips, n_frames, audio, (cudaStream_t)stream);
+    return adn::launch_istft(mag, phasor_c64, spec_is_complex, seed, nullptr, n_clips, n_frames, audio, (cudaStream_t)stream);
+}
+
+extern "C" int adn_istft_ola_counter_f32(const float* mag, uint64_t seed, const uint64_t* seed_counter_dev, int64_t n_clips,
+                                         int64_t n_frames, float* audio, void* stream) {
+    if (!seed_counter_dev) return ADN_ERR_ARG;
+    return adn::launch_istft(mag, nullptr, 0, seed, seed_counter_dev, n_clips, n_frames, audio, (cudaStream_t)stream);
+}
+
+extern "C" int adn_u64_add(uint64_t* counter_dev, uint64_t inc, void* stream) {
+    if (!counter_dev) return ADN_ERR_ARG;
+    int st = adn::check_device();
+    if (st != ADN_OK) return st;
+    adn::u64_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<unsigned long long*>(counter_dev), (unsigned long long)inc);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
 }
 
 extern "C" int adn_random_phasor_c64(uint64_t seed, int64_t n_clips, int64_t n_frames, float* phasor_c64, void* stream) {

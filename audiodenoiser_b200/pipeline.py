@@ -31,6 +31,13 @@ class Denoiser:
         self.use_graph = bool(use_graph)
         self._graphs = {}
         self.launches_per_call = None
+        # Random-phase reconstruction draws a FRESH phase per call, as test.py:36 does: call k uses seed + k.  The per-call part
+        # lives in a device counter (advanced by a one-thread kernel at the end of every call, inside the captured graph too),
+        # because a graph replay bakes kernel arguments in.  `last_seed` is the effective seed of the most recent call:
+        # spectral.random_phasor(last_seed, ...) reproduces its phasor.
+        self.calls = 0
+        self.last_seed = self.seed
+        self._counter = None
 
     def denoise(self, wave: torch.Tensor, phasor: torch.Tensor | None = None, return_spectrograms: bool = False):
         """wave (N, L) float32 -> audio (N, 128*(T-1)) float32 CUDA.  ``wave`` is a CUDA tensor, or a (pinned) host tensor
@@ -48,6 +55,7 @@ class Denoiser:
                 wave = wave.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
             wave = wave.contiguous()
             audio, mag, den = self._run(wave, phasor)
+            self._count_call(phasor)
             return (audio, mag, den) if return_spectrograms else audio
         dev = wave.device if wave.is_cuda else torch.device("cuda", torch.cuda.current_device())
         key = (tuple(wave.shape), str(dev), phasor is not None, self.phase, self.model._version_key(dev))
@@ -60,9 +68,15 @@ class Denoiser:
             if phasor is not None:
                 g["phasor"].copy_(phasor.to(torch.complex64), non_blocking=True)
             g["graph"].replay()
+        self._count_call(phasor)
         if return_spectrograms:
             return g["audio"], g["mag"], g["den"]
         return g["audio"]
+
+    def _count_call(self, phasor):
+        if phasor is None and self.phase == "random":
+            self.last_seed = self.seed + self.calls
+            self.calls += 1
 
     def _run(self, wave, phasor):
         if self.input_sr and (self.input_sr != resample.SAMPLE_RATE or wave.dim() == 3):
@@ -72,9 +86,27 @@ class Denoiser:
             mag = spec.abs()
             den = self.model(mag.unsqueeze(1)).squeeze(1)
             return spectral.istft_batched(den, phase_from=spec), mag, den
+        nvtx = torch.cuda.nvtx                               # ranges for nsys / ncu timelines; no-ops otherwise
+        nvtx.range_push("adn.stft_mag")
         mag = spectral.stft_mag_batched(wave, self.center)
+        nvtx.range_pop()
+        nvtx.range_push("adn.unet_forward")
         den = self.model(mag.unsqueeze(1)).squeeze(1)
-        return spectral.istft_batched(den, phasor, seed=self.seed), mag, den
+        nvtx.range_pop()
+        nvtx.range_push("adn.istft_ola")
+        try:
+            return self._reconstruct(den, phasor, wave.device), mag, den
+        finally:
+            nvtx.range_pop()
+
+    def _reconstruct(self, den, phasor, device):
+        if phasor is not None:
+            return spectral.istft_batched(den, phasor)
+        if self._counter is None or self._counter.device != device:
+            self._counter = torch.full((1,), self.calls, dtype=torch.int64, device=device)
+        audio = spectral.istft_batched(den, None, seed=self.seed, seed_counter=self._counter)
+        spectral.advance_counter(self._counter)
+        return audio
 
     def _capture(self, wave, phasor):
         dev = wave.device
@@ -89,6 +121,8 @@ class Denoiser:
                     audio, mag, den = self._run(static_wave, static_ph)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
+            if self._counter is not None:
+                self._counter.fill_(self.calls)            # the warm-up calls advanced the device counter: they do not count
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 audio, mag, den = self._run(static_wave, static_ph)

@@ -85,13 +85,15 @@ def stft_complex_batched(wave, center: bool = True):
     return out
 
 
-def istft_batched(mag, phasor=None, seed: int = 0, out=None, phase_from=None):
+def istft_batched(mag, phasor=None, seed: int = 0, out=None, phase_from=None, seed_counter=None):
     """Inverse STFT + overlap-add: (N,257,T) magnitude x (N,257,T) complex64 unit phasor -> (N, 128*(T-1)) float32.
 
     ``phasor=None`` draws a uniform random phase on the device from ``seed`` (test.py:36 uses the unseeded numpy RNG).
     A complex ``mag`` is taken as the complex spectrogram itself (librosa.istft at test.py:40).
     ``phase_from`` (opt-in, NOT the reference's behaviour): a complex (N,257,T) spectrogram whose phase is used, i.e. the
-    kernel inverts ``mag * phase_from / |phase_from|`` (denoised magnitude + noisy phase)."""
+    kernel inverts ``mag * phase_from / |phase_from|`` (denoised magnitude + noisy phase).
+    ``seed_counter``: a 1-element int64 CUDA tensor added to ``seed`` on the device (random-phase mode only), so that replays of a
+    captured CUDA graph still draw a fresh phase per call; advance it with ``advance_counter``."""
     torch = _lib.require_cuda()
     if not isinstance(mag, torch.Tensor) or not mag.is_cuda:
         raise _lib.AdnError("expected a CUDA tensor (no CPU fallback)")
@@ -135,10 +137,24 @@ def istft_batched(mag, phasor=None, seed: int = 0, out=None, phase_from=None):
     elif tuple(out.shape) != (n, n_out) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be a contiguous float32 (N, 128*(T-1)) tensor")
     with torch.cuda.device(mag.device):
-        st = _lib.load().adn_istft_ola_f32(mag_ptr, ph_ptr, mode, int(seed) & 0xFFFFFFFFFFFFFFFF, n, t,
-                                           out.data_ptr(), _lib.stream_ptr())
+        if seed_counter is not None and mode == 0 and ph_ptr == 0:
+            if seed_counter.dtype != torch.int64 or not seed_counter.is_cuda or seed_counter.numel() != 1:
+                raise ValueError("seed_counter must be a 1-element int64 CUDA tensor")
+            st = _lib.load().adn_istft_ola_counter_f32(mag_ptr, int(seed) & 0xFFFFFFFFFFFFFFFF, seed_counter.data_ptr(), n, t,
+                                                       out.data_ptr(), _lib.stream_ptr())
+        else:
+            st = _lib.load().adn_istft_ola_f32(mag_ptr, ph_ptr, mode, int(seed) & 0xFFFFFFFFFFFFFFFF, n, t,
+                                               out.data_ptr(), _lib.stream_ptr())
     _lib.check(st, "adn_istft_ola_f32")
     return out
+
+
+def advance_counter(counter, inc: int = 1):
+    """counter += inc on the device with a one-thread kernel of the library (capturable into a CUDA graph)."""
+    torch = _lib.require_cuda()
+    with torch.cuda.device(counter.device):
+        _lib.check(_lib.load().adn_u64_add(counter.data_ptr(), int(inc), _lib.stream_ptr()), "adn_u64_add")
+    return counter
 
 
 def random_phasor(seed: int, n_clips: int, n_frames: int, device=None):

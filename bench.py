@@ -355,9 +355,10 @@ def run_b200(args):
             idx = [i % uniq for i in range(batch)]
             gain = np.array([1.0 - 0.25 * ((i // uniq) % 3) / 3.0 for i in range(batch)], np.float32)[:, None]
             wave1 = torch.from_numpy(np.stack(noisy)[idx] * gain).to(dev)
-            solo = Denoiser(net, center=True, seed=1234 + other, use_graph=False).denoise(wave1)
+            k = den.last_seed - den.seed                          # every rank has made the same number of calls: call k used seed + k
+            solo = Denoiser(net, center=True, seed=1234 + other + k, use_graph=False).denoise(wave1)
             rows = gathered[other * batch:(other + 1) * batch]
-            own = Denoiser(net, center=True, seed=1234, use_graph=False).denoise(dev_batches[0])
+            own = Denoiser(net, center=True, seed=1234 + k, use_graph=False).denoise(dev_batches[0])
             gather_check = {"what": "all_gather rows of rank 1 (and rank 0's own rows) vs a single-GPU recomputation on rank 0",
                             "rows_checked": int(2 * batch), "bit_equal": bool(torch.equal(rows, solo) and torch.equal(gathered[:batch], own)),
                             "max_abs_diff": float(max((rows - solo).abs().max(), (gathered[:batch] - own).abs().max()))}
@@ -445,7 +446,7 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         seed0 = 1234 + rank
         a0, m0, d0 = eager.denoise(dev_batches[0], return_spectrograms=True)
-        ph0 = spectral.random_phasor(seed0, batch, t_frames, dev)[0].cpu().numpy()
+        ph0 = spectral.random_phasor(eager.last_seed, batch, t_frames, dev)[0].cpu().numpy()
         clean0 = synth.make_clip((rank * rot + 0) * uniq + 0, args.variant, return_clean=True)[1]
         parity = parity_on_benchmark_clip(host_batches[0][0].numpy(), clean0, sd, seed0, m0[0].cpu().numpy(), d0[0].cpu().numpy(),
                                           a0[0].cpu().numpy(), ph0)

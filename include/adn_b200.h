@@ -89,6 +89,14 @@ int adn_stft_complex_f32(const float* wave, int64_t n_clips, int64_t length, int
 int adn_istft_ola_f32(const float* mag, const float* phasor_c64, int spec_is_complex, uint64_t seed,
                       int64_t n_clips, int64_t n_frames, float* audio, void* stream);
 
+/* The random-phase form of adn_istft_ola_f32 with a DEVICE-side call counter: the phase is drawn from seed + *seed_counter_dev.
+ * test.py:36 draws a fresh phase per call; a CUDA-graph replay bakes kernel arguments in, so the per-call part of the seed lives in
+ * device memory and is advanced inside the same graph by adn_u64_add (one thread).  adn_random_phasor_c64(seed + counter) exports
+ * the phasor of any call. */
+int adn_istft_ola_counter_f32(const float* mag, uint64_t seed, const uint64_t* seed_counter_dev, int64_t n_clips, int64_t n_frames,
+                              float* audio, void* stream);
+int adn_u64_add(uint64_t* counter_dev, uint64_t inc, void* stream);
+
 /* The unit phasor adn_istft_ola_f32 generates for `seed` when phasor == NULL, written out as (n_clips,257,T) complex64:
  * the device-side stand-in for `angles = np.exp(2j * np.pi * np.random.rand(*mag.shape))` (test.py:36).  Lets a caller
  * (and the parity tests) reproduce a seeded reconstruction with an explicit phasor, bit for bit. */
