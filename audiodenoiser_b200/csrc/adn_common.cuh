@@ -9,6 +9,9 @@ namespace adn {
 
 void set_last_cuda_error(cudaError_t e);   // abi.cu (thread-local)
 int check_device();                        // abi.cu: ADN_OK iff current device is sm_100
+// conv_c1_tc.cu: first-layer conv (Cin = 1) as a TF32 tcgen05 implicit GEMM; ADN_ERR_ARG when the output cannot take a TMA store
+int conv3x3_c1_tc(const float* x, int n, int h, int w, const float* weight, const float* scale, const float* shift, float relu_floor,
+                  void* out, cudaStream_t stream);
 
 #define ADN_CUDA_TRY(expr)                                  \
     do {                                                    \
@@ -50,9 +53,10 @@ inline cudaError_t ensure_dyn_smem(K kernel, int bytes, unsigned char* flags) {
 
 // ---------------------------------------------------------------- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2)
 // A complex number IS a float2, so every complex add / scale is one packed instruction.  The packed instructions run at the
-// same lane rate as their scalar forms (measured, scripts/microbench/fp32x2_rate.cu) but take HALF the issue slots, and their
-// operand modifiers (half swap, per-half negation, scalar broadcast) make the x(-i) rotations and the real-by-complex
-// products of an FFT free: ptxas folds make_float2(a.y, -a.x) style operands into the instruction.
+// same lane rate as their scalar forms (scripts/microbench/fp32x2_rate.cu) and -- round-2 measurement, scripts/microbench/
+// issue_mix.cu -- hold the ISSUE PORT for two cycles as well: nothing co-issues beside them, so they halve the instruction count,
+// not the issue slots.  What they do buy: operand modifiers (half swap, per-half negation, scalar broadcast) make the x(-i)
+// rotations and the real-by-complex products of an FFT free (ptxas folds make_float2(a.y, -a.x) style operands into the instruction).
 typedef unsigned long long pk64;
 __device__ __forceinline__ pk64 pk_bits(float2 a) { return *reinterpret_cast<pk64*>(&a); }
 __device__ __forceinline__ float2 pk_val(pk64 a) { return *reinterpret_cast<float2*>(&a); }

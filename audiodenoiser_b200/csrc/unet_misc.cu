@@ -1,6 +1,7 @@
 // unet_misc.cu -- the HBM-bound pieces around the tcgen05 convolutions of the reference UNet (code/model.py):
 // checkpoint packing, BN folding, the Cin=1 first layer (direct conv), 2x2 max-pool, layout converters, the
 // SpectrogramDataset transform (code/data_loader.py:41-72) and error statistics.
+#include <cstdlib>
 #include "adn_common.cuh"
 
 namespace adn {
@@ -392,10 +393,17 @@ static void launch_c1(const float* x, int n, int h, int w, const float* weight, 
     else          launch_c1_run<4>(x, n, h, w, weight, scale, shift, relu_floor, out, stream);
 }
 
+// ADN_C1_IMPL=fma keeps the CUDA-core first-layer kernel (A/B measurements); default: the TF32 tensor-core kernel of conv_c1_tc.cu
+static bool c1_use_tc() {
+    static const bool v = !(getenv("ADN_C1_IMPL") && getenv("ADN_C1_IMPL")[0] == 'f');
+    return v;
+}
+
 extern "C" int adn_conv3x3_c1_bn_relu_bf16(const float* x, int n, int h, int w, const float* weight, const float* scale,
                                            const float* shift, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
+    if (c1_use_tc() && conv3x3_c1_tc(x, n, h, w, weight, scale, shift, 0.f, out, (cudaStream_t)stream) == ADN_OK) return ADN_OK;
     launch_c1(x, n, h, w, weight, scale, shift, 0.f, (uint4*)out, (cudaStream_t)stream);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -406,6 +414,7 @@ extern "C" int adn_conv3x3_c1_affine_bf16(const float* x, int n, int h, int w, c
                                           const float* shift, int relu, void* out, void* stream) {
     if (!x || !weight || !scale || !shift || !out || n <= 0 || h <= 0 || w <= 0) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
+    if (c1_use_tc() && conv3x3_c1_tc(x, n, h, w, weight, scale, shift, relu ? 0.f : -INFINITY, out, (cudaStream_t)stream) == ADN_OK) return ADN_OK;
     launch_c1(x, n, h, w, weight, scale, shift, relu ? 0.f : -INFINITY, (uint4*)out, (cudaStream_t)stream);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
