@@ -455,6 +455,26 @@ extern "C" int adn_spec_f16_crop_f32(const float* src, int64_t n, int f_in, int 
     return ADN_OK;
 }
 
+// sums[3] = element count, sums[4] = clip count, sums[5..7] = clip count x (stft, mel, l1) loss terms: the bookkeeping slots of the
+// statistics vector that sharding.ShardedDenoiser all-reduces, written by one thread (no eager framework kernels on the path)
+__global__ void stats_pack_kernel(double* __restrict__ sums, double numel, double n_clips, const float* __restrict__ loss4) {
+    sums[3] = numel;
+    if (loss4 != nullptr) {
+        sums[4] = n_clips;
+        sums[5] = n_clips * (double)loss4[1];
+        sums[6] = n_clips * (double)loss4[2];
+        sums[7] = n_clips * (double)loss4[3];
+    }
+}
+
+extern "C" int adn_stats_pack_f64(double* sums8, int64_t numel, int64_t n_clips, const float* loss4, void* stream) {
+    if (!sums8 || numel < 0 || n_clips < 0) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    stats_pack_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sums8, (double)numel, (double)n_clips, loss4);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
 extern "C" int adn_spec_error_sums_f64(const float* pred, const float* target, int64_t count, double* sums, void* stream) {
     if (count < 0 || !sums) return ADN_ERR_ARG;
     if (count == 0) return ADN_OK;

@@ -158,6 +158,10 @@ class CombinedPerceptualLoss(nn.Module):
         self.w_mel = 0.4
         self.w_l1 = 0.2
 
+    def values(self, pred, target):
+        """The four values as ONE device (or host) 4-vector (total, stft, mel, l1) -- what forward() unpacks."""
+        return _values(pred, target)
+
     def forward(self, pred, target):
         out = _values(pred, target)
         if (self.w_stft, self.w_mel, self.w_l1) != (0.4, 0.4, 0.2):      # weights edited after construction

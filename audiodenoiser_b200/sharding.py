@@ -213,14 +213,15 @@ class ShardedDenoiser:
         with torch.cuda.device(p.device):
             st = _lib.load().adn_spec_error_sums_f64(p.data_ptr(), t.data_ptr(), p.numel(), self._sums.data_ptr(), _lib.stream_ptr())
         _lib.check(st, "adn_spec_error_sums_f64")
-        self._sums[3] = float(p.numel())
+        loss4 = None
         if self.with_loss and p.shape[-1] > 31:
             # CombinedPerceptualLoss of this shard (test.py:118-122), weighted by its clip count so the reduced value is the
             # full-batch mean the reference would print
-            terms = self._criterion(p.unsqueeze(1) if p.dim() == 3 else p, t.unsqueeze(1) if t.dim() == 3 else t)
-            n = float(p.shape[0])
-            self._sums[4] = n
-            self._sums[5:8] = torch.stack(terms[1:]).double() * n
+            loss4 = self._criterion.values(p.unsqueeze(1) if p.dim() == 3 else p, t.unsqueeze(1) if t.dim() == 3 else t)
+        with torch.cuda.device(p.device):
+            st = _lib.load().adn_stats_pack_f64(self._sums.data_ptr(), p.numel(), p.shape[0], loss4.data_ptr() if loss4 is not None else 0,
+                                                _lib.stream_ptr())
+        _lib.check(st, "adn_stats_pack_f64")
         return self._sums
 
     def finish(self):

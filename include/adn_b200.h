@@ -186,6 +186,10 @@ int adn_spec_f16_crop_f32(const float* src, int64_t n, int f_in, int t_in, int f
  * sums[0] += sum|pred-target|, sums[1] += sum target^2, sums[2] += sum (target-pred)^2, over `count` elements.
  * sums is a device array of 3 doubles that the caller zeroes. */
 int adn_spec_error_sums_f64(const float* pred, const float* target, int64_t count, double* sums, void* stream);
+/* The bookkeeping slots of the same 8-double statistics vector: sums8[3] = numel, and when loss4 (the device 4-vector of
+ * adn_combined_loss_f32: total, stft, mel, l1 -- test.py:118-122) is given, sums8[4] = n_clips, sums8[5..7] = n_clips x the three terms,
+ * so that the all-reduced vector yields exact full-batch means for unequal shards. */
+int adn_stats_pack_f64(double* sums8, int64_t numel, int64_t n_clips, const float* loss4, void* stream);
 
 /* CombinedPerceptualLoss.forward (loss.py:83-95) = 0.4 * MultiScaleSTFTLoss (loss.py:12-35) + 0.4 * MelSpectrogramLoss
  * (loss.py:44-69) + 0.2 * L1Loss (loss.py:76,86) on (batch,1,freq,frames) float32 magnitude tensors (test.py:118-122,
