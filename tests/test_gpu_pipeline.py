@@ -117,3 +117,33 @@ def test_native_rate_input_is_resampled_on_the_device(net):
         assert torch.equal(mag, ref_mag) and torch.equal(audio, ref_audio)
     with pytest.raises(ValueError):
         Denoiser(net, use_graph=False).denoise(native)
+
+
+def test_peer_gather_single_rank_group():
+    """sharding.PeerGather (copy-engine all-gather into torch symmetric-memory buffers) on a ONE-rank NCCL group: rendezvous,
+    peer-buffer views, own-slot copy, device barrier, double buffering.  The multi-rank data path is checked on hardware by
+    bench.py (`gather_check`: rank 0 recomputes rank 1's shard, rows must be bit-equal) and its host logic by the gloo tests."""
+    import os
+    import torch.distributed as dist
+    from audiodenoiser_b200.sharding import PeerGather
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev())
+    try:
+        if not PeerGather.available(dev()):
+            pytest.skip("symmetric memory unavailable")
+        try:
+            pg = PeerGather(4, (1000,), torch.float32, dev())
+        except Exception as exc:  # noqa: BLE001
+            pytest.skip(f"symmetric memory rendezvous failed on this box: {exc}")
+        a = torch.arange(4000, dtype=torch.float32, device=dev()).reshape(4, 1000)
+        g0 = pg.start(a, 4)
+        g1 = pg.start(a * 2, 4)
+        g2 = pg.start(a * 3, 4)            # reuses the first buffer: waits for its gather first
+        pg.finish()
+        torch.cuda.synchronize()
+        assert torch.equal(g1, a * 2) and torch.equal(g2, a * 3) and g0.data_ptr() == g2.data_ptr()
+    finally:
+        dist.destroy_process_group()
