@@ -130,7 +130,10 @@ def test_peer_gather_single_rank_group():
         pytest.skip("a process group already exists in this process")
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29577")
-    dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev())
+    try:
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev())
+    except Exception as exc:  # noqa: BLE001  (port taken, NCCL unavailable ...): not what this test is about
+        pytest.skip(f"cannot create a one-rank NCCL group here: {exc}")
     try:
         if not PeerGather.available(dev()):
             pytest.skip("symmetric memory unavailable")
