@@ -364,9 +364,15 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// TFIX: the frame count T as a compile-time constant (0 = run-time).  For the three shapes the reference scripts produce -- 188
+// (create_test_dataset.py, 3 s @ 8 kHz), 122 (create_train_dataset.py chunks), 1034 (3 s @ 44.1 kHz) -- the 32 row addresses of a
+// thread's stores are then `base + immediate`: no address instruction at all (the pointer chains of the generic path cost 64 of
+// ~1 350 issue slots per warp-tile).
+template <int TFIX>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 stft_ws_kernel(const float* __restrict__ wave, long long n_clips, int length, long long clip_stride, int center,
-               int n_frames, int tiles_per_clip, float* __restrict__ out) {
+               int n_frames_rt, int tiles_per_clip, float* __restrict__ out) {
+    const int n_frames = TFIX ? TFIX : n_frames_rt;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* const samples = reinterpret_cast<float*>(smem_raw);                                     // [slot][hop][130]
     float2* const work0 = reinterpret_cast<float2*>(smem_raw + WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES);   // [buf][k1*16 + n2][frame]
@@ -511,21 +517,32 @@ stft_ws_kernel(const float* __restrict__ wave, long long n_clips, int length, lo
             const float4* twa = reinterpret_cast<const float4*>(s_tw512 + a * 16);        // W512^(a + 16 k2), two per load
             if (w != 0) {
                 float* pa = out + row0 + (long long)a * n_frames;                         // rows a + 16 k2, upwards
-                float* pb = out + row0 + (long long)(b + 240) * n_frames;                 // rows b + 16 k2, downwards from k2 = 15
+                float* pb = out + row0 + (long long)b * n_frames;                         // rows b + 16 k2 (TFIX) / from k2 = 15 downwards
+                if (!TFIX) pb += 15 * step;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {                                             // 256 - k = b + 16 (15 - k2)
                     const float4 t4 = twa[j];
                     split(make_float2(t4.x, t4.y), A[2 * j], B[15 - 2 * j]);
                     split(make_float2(t4.z, t4.w), A[2 * j + 1], B[14 - 2 * j]);
                     const float m0 = mag(A[2 * j]), m1 = mag(B[15 - 2 * j]), m2 = mag(A[2 * j + 1]), m3 = mag(B[14 - 2 * j]);
-                    if (live) {
-                        __stcs(pa, m0);
-                        __stcs(pb, m1);
-                        __stcs(pa + step, m2);
-                        __stcs(pb - step, m3);
+                    if (TFIX) {                                                           // immediate offsets from two base pointers
+                        constexpr long long ST = 16LL * TFIX;
+                        if (live) {
+                            __stcs(pa + (2 * j) * ST, m0);
+                            __stcs(pb + (15 - 2 * j) * ST, m1);
+                            __stcs(pa + (2 * j + 1) * ST, m2);
+                            __stcs(pb + (14 - 2 * j) * ST, m3);
+                        }
+                    } else {
+                        if (live) {
+                            __stcs(pa, m0);
+                            __stcs(pb, m1);
+                            __stcs(pa + step, m2);
+                            __stcs(pb - step, m3);
+                        }
+                        pa += 2 * step;
+                        pb -= 2 * step;
                     }
-                    pa += 2 * step;
-                    pb -= 2 * step;
                 }
             } else {
                 const float4* twb = reinterpret_cast<const float4*>(s_tw512 + 8 * 16);    // W512^(8 + 16 k2)
@@ -579,11 +596,20 @@ static int launch_stft(const float* wave, int64_t n_clips, int64_t length, int64
         ADN_CUDA_TRY(cudaMemsetAsync(crop, 0, (size_t)n_clips * f_out * t_out * sizeof(float), stream));
     static const int impl = getenv("ADN_STFT_IMPL") ? atoi(getenv("ADN_STFT_IMPL")) : 2;        // 1: barrier-phased CTAs, 2: warp-specialised
     if (impl == 2 && !COMPLEX_OUT && !CROP) {
-        static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(stft_ws_kernel, WS_SMEM_BYTES, smem_set));
         const long long sms = num_sms();
         const int grid = (int)(total < sms ? total : sms);          // persistent: one 16-warp CTA per SM
-        stft_ws_kernel<<<grid, WS_THREADS, WS_SMEM_BYTES, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, tiles_per_clip, out);
+#define ADN_WS_LAUNCH(TF_)                                                                                                          \
+        do {                                                                                                                        \
+            static unsigned char smem_set[64] = {0};                                                                                \
+            ADN_CUDA_TRY(ensure_dyn_smem(stft_ws_kernel<TF_>, WS_SMEM_BYTES, smem_set));                                            \
+            stft_ws_kernel<TF_><<<grid, WS_THREADS, WS_SMEM_BYTES, stream>>>(wave, n_clips, (int)length, clip_stride, center, (int)T, \
+                                                                            tiles_per_clip, out);                                  \
+        } while (0)
+        if (T == 188) ADN_WS_LAUNCH(188);
+        else if (T == 1034) ADN_WS_LAUNCH(1034);
+        else if (T == 122) ADN_WS_LAUNCH(122);
+        else ADN_WS_LAUNCH(0);
+#undef ADN_WS_LAUNCH
         ADN_LAUNCH_CHECK();
         return ADN_OK;
     }
