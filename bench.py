@@ -197,9 +197,13 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 STFT/iSTFT + f32 UNet (CPU)", "data": "synthetic",
-        "config": {**workload_config(args, t_frames, per_step),
-                   "note": f"reference arm: ONE CPU process on this box's {cores} host cores, {per_step} clip(s) per step (a bounded sample of the "
-                           f"b200 arm's {args.batch}-clip batches); at --gpus N > 1 it is still this one host process -- the reference has no multi-device path"},
+        # the b200 arm's workload, as the contract asks; what ONE STEP of this arm really processes is stated beside it
+        "config": {**workload_config(args, t_frames, args.batch),
+                   "l2": "n/a (CPU arm)", "collectives": "none (one CPU process)",
+                   "clips_timed_per_step": per_step,
+                   "note": f"reference arm: ONE CPU process on this box's {cores} host cores; every step times {per_step} clip(s), a bounded sample of the "
+                           f"{args.batch}-clip batch the b200 arm processes per GPU and step (value = audio-seconds of the timed clips / their time); at "
+                           f"--gpus N > 1 it is still this one host process -- the reference has no multi-device path"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} clip(s)/step x {args.steps} steps, variant {args.variant}: float64 STFT -> fp32 torch-CPU UNet "
                                    f"({torch.get_num_threads()} threads) -> {GL_ITERATIONS}-iteration istft/stft loop + istft"},
