@@ -126,7 +126,18 @@ channel_reduce_kernel(const RedArgs a) {
 __device__ __forceinline__ double fold_partials(const float* partial, int nb, int ns, int c, int slot, int ch) {
     const int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = lane; b < nb; b += 32) s += (double)partial[((long long)b * ns + slot) * c + ch];
+    // eight loads in flight per lane (a one-at-a-time loop made each finalise launch cost 5-7 us of pure memory latency); the
+    // additions keep the ascending block order, so the result is bit-identical to the sequential loop
+    for (int b0 = lane; b0 < nb; b0 += 32 * 8) {
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int b = b0 + 32 * j;
+            v[j] = b < nb ? partial[((long long)b * ns + slot) * c + ch] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += (double)v[j];
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     return s;

@@ -191,7 +191,13 @@ wgrad_reduce_kernel(const WgradArgs a) {
             const float* p = a.partial + (long long)m * a.n_pad + n;
             for (int t = 0; t < all_taps; ++t) {
                 float acc = 0.f;
-                for (int s = 0; s < a.splits; ++s) acc += p[((long long)s * all_taps + t) * plane];
+                for (int s0 = 0; s0 < a.splits; s0 += 4) {             // four loads in flight; additions stay in ascending split order
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = s0 + j < a.splits ? p[((long long)(s0 + j) * all_taps + t) * plane] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc += v[j];
+                }
                 s_out[threadIdx.x * all_taps + t] = acc;
             }
         }
@@ -221,7 +227,13 @@ wgrad_reduce_splits_kernel(const WgradArgs a) {
         float acc = 0.f;
         if (n < a.n_total) {
             const float* p = a.partial + (long long)t * plane + (long long)m * a.n_pad + n;
-            for (int s = ty; s < a.splits; s += 4) acc += p[(long long)s * all_taps * plane];
+            for (int s0 = ty; s0 < a.splits; s0 += 32) {               // eight loads in flight; additions stay in ascending split order
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = s0 + 4 * j < a.splits ? p[(long long)(s0 + 4 * j) * all_taps * plane] : 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc += v[j];
+            }
         }
         s_part[ty][tx] = acc;
         __syncthreads();
