@@ -331,35 +331,6 @@ constexpr int WS_THREADS = 512;
 constexpr int WS_SAMPLE_SLOTS = 3;
 constexpr int WS_SMEM_BYTES = WS_SAMPLE_SLOTS * ST_SAMPLES_BYTES + 2 * ST_WORK_BYTES + ST_TABLE_BYTES + 128;
 
-// mbarrier wait for the spectral kernels: try_wait suspends the warp in hardware until the phase flips (or a system time limit
-// passes), so the loop body is as small as possible -- in an issue-bound kernel every polling instruction is taken from a warp that
-// has arithmetic to issue.  Bounded: a barrier that never flips is a protocol bug and traps instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-    for (int spin = 0; spin < (1 << 22); ++spin) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    __trap();
-}
-
-// (clip, tile-in-clip) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: advanced with adds instead of a division per tile
-struct TileWalk {
-    int clip, tin, dq, dr, tpc;
-    __device__ __forceinline__ void init(int first, int step, int tiles_per_clip) {
-        tpc = tiles_per_clip; clip = first / tpc; tin = first - clip * tpc; dq = step / tpc; dr = step - dq * tpc;
-    }
-    __device__ __forceinline__ void next() {
-        clip += dq; tin += dr;
-        if (tin >= tpc) { tin -= tpc; ++clip; }
-    }
-};
-
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }

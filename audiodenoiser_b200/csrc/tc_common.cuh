@@ -46,6 +46,35 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
+// mbarrier wait for the spectral kernels: try_wait suspends the warp in hardware until the phase flips (or a system time limit
+// passes), so the loop body is as small as possible -- in an issue-bound kernel every polling instruction is taken from a warp that
+// has arithmetic to issue.  Bounded: a barrier that never flips is a protocol bug and traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// (clip, tile-in-clip) of the tiles blockIdx.x, blockIdx.x + gridDim.x, ...: advanced with adds instead of a division per tile
+struct TileWalk {
+    int clip, tin, dq, dr, tpc;
+    __device__ __forceinline__ void init(int first, int step, int tiles_per_clip) {
+        tpc = tiles_per_clip; clip = first / tpc; tin = first - clip * tpc; dq = step / tpc; dr = step - dq * tpc;
+    }
+    __device__ __forceinline__ void next() {
+        clip += dq; tin += dr;
+        if (tin >= tpc) { tin -= tpc; ++clip; }
+    }
+};
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Driver for ncu captures of the spectral kernels at BASELINE config 2 (4 096 clips, 3 s @ 8 kHz): 3 STFT + 3 iSTFT launches.
-usage: ncu --set full -k regex:stft_kernel -s 2 -c 1 ... python scripts/prof_spectral.py [n_clips]"""
+"""Driver for ncu captures of the spectral kernels at BASELINE config 2 (4 096 clips, 3 s @ 8 kHz): 3 STFT launches, 3 iSTFT
+launches with the in-kernel phase and 3 with an explicit phasor.
+usage: ncu --set full -k regex:stft_ws_kernel -s 2 -c 1 ... python scripts/prof_spectral.py [n_clips]"""
 import os
 import sys
 
@@ -19,5 +20,8 @@ for i in range(3):
     spectral.stft_mag_batched(x, True, out=mag)
 for i in range(3):
     spectral.istft_batched(mag, None, seed=i, out=audio)
+ph = torch.polar(torch.ones_like(mag), torch.rand_like(mag) * 6.2831853)
+for i in range(3):
+    spectral.istft_batched(mag, ph, out=audio)
 torch.cuda.synchronize()
 print("ok")

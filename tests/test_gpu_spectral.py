@@ -121,8 +121,10 @@ def test_random_phase_is_seeded_and_deterministic():
 
 
 def test_random_phase_mode_equals_explicit_phasor():
-    """The in-kernel phase generator is exported (adn_random_phasor_c64): seeded mode == explicit-phasor mode bit for bit,
-    the phasor has unit modulus and uniform phase, and the result matches the oracle istft of mag * phasor."""
+    """The in-kernel phase generator is exported (adn_random_phasor_c64): seeded mode == explicit-phasor mode (to rounding: the
+    seeded mode runs the warp-specialised kernel, the explicit-phasor modes the barrier-phased one -- same arithmetic, different
+    fused-multiply-add contraction), the phasor has unit modulus and uniform phase, and the result matches the oracle istft of
+    mag * phasor."""
     rng = np.random.default_rng(5)
     mag = torch.from_numpy(np.abs(rng.standard_normal((3, 257, 70))).astype(np.float32)).to(dev())
     ph = spectral.random_phasor(42, 3, 70)
@@ -133,7 +135,7 @@ def test_random_phase_mode_equals_explicit_phasor():
     assert not torch.equal(ph[0], ph[1])                                   # clips get distinct phases
     a = spectral.istft_batched(mag, None, seed=42)
     b = spectral.istft_batched(mag, ph)
-    assert torch.equal(a, b)
+    assert float((a - b).abs().max()) <= 2e-6 * float(b.abs().max())
     ref = so.istft(mag[1].cpu().numpy().astype(np.float64) * ph[1].cpu().numpy().astype(np.complex128))
     assert np.max(np.abs(a[1].cpu().numpy() - ref)) <= 1e-5 * np.max(np.abs(ref))
 
