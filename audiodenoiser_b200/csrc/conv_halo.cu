@@ -22,9 +22,11 @@
 namespace adn {
 
 constexpr int H_TW = 8, H_TH = 16;                 // pixel tile: 16 rows x 8 columns = 128 GEMM rows
-constexpr int H_PITCH = 16;                        // halo row pitch in pixels (2048 B: a multiple of the 1024-B swizzle atom)
 constexpr int H_ROWS = H_TH + 2;
-constexpr int H_A_STAGE = H_ROWS * H_PITCH * 128;  // 36 864 B
+// halo row pitch in pixels: 10 = the dense 18 x 10 halo tile (the swizzle follows absolute address bits, so 8-pixel row groups may
+// start at any 128-byte offset and SBO = 1280 B works), 16 = rows padded to two 1024-B atoms (the first version)
+constexpr int h_a_bytes(int pitch) { return H_ROWS * pitch * 128; }
+constexpr int h_a_stage(int pitch) { return (h_a_bytes(pitch) + 1023) & ~1023; }
 constexpr int H_THREADS = 224;
 constexpr int H_EPI_THREADS = 128;
 constexpr int H_MAX_A = 8, H_MAX_B = 16;
@@ -53,7 +55,7 @@ struct HaloArgs {
     float* head_out;
 };
 
-template <int BLOCK_N, bool B_RESIDENT, int NCTA>
+template <int BLOCK_N, bool B_RESIDENT, int NCTA, int H_PITCH>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -62,6 +64,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // loads its own halo tile and HALF of the weight block, so the shared-memory operand traffic per CTA and MMA drops from
     // A + B to A + B/2 bytes -- the single-CTA kernel was measured at the smem->tensor-core operand bandwidth (~64 B/clk).
     constexpr bool PAIR = (NCTA == 2);
+    constexpr int H_A_STAGE = h_a_stage(H_PITCH), H_A_BYTES = h_a_bytes(H_PITCH);
     constexpr int B_ROWS = BLOCK_N / NCTA;                         // weight rows held by this CTA
     constexpr int B_BLOCK = B_ROWS * 128;                          // bytes of one (tap, chunk) weight block in this CTA
     constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
@@ -143,7 +146,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 const int x0 = tx * H_TW - 1, y0 = ty * H_TH - 1;
                 for (int ch = 0; ch < chunks; ++ch) {
                     mbar_wait(empty_a(stage), phase ^ 1u);
-                    if (leader) mbar_arrive_expect_tx(full_a(stage), NCTA * H_A_STAGE);
+                    if (leader) mbar_arrive_expect_tx(full_a(stage), NCTA * H_A_BYTES);
                     const uint32_t dst = a_base + (uint32_t)stage * H_A_STAGE;
                     const CUtensorMap* map = (ch < a.c0_chunks) ? &tmA0 : &tmA1;
                     const int c = (ch < a.c0_chunks ? ch : ch - a.c0_chunks) * 64;
@@ -407,12 +410,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 
 // ------------------------------------------------------------------------------------------------ host side
 static int g_dx_mode = 1;        // 0: never use the kx-in-N kernel of conv_dx.cu for the 64-output-channel layers
-static int g_pair_mode = 1;      // 0: never use CTA pairs; 1: where the layer is shared-memory-operand bound and a pair pays off
+static int g_pair_mode = 3;      // 0: never use CTA pairs; 1: where the layer is shared-memory-operand bound and a pair pays off; 3: also the 256-wide layers
+static int g_halo_pitch = 10;    // 10: dense halo tile; 16: padded rows
+static int g_halo_stages = 0;    // > 0: A stages of the streaming-B configuration (tuning hook)
 
-template <int BLOCK_N, int NCTA>
+template <int BLOCK_N, int NCTA, int H_PITCH>
 static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const CUtensorMap& mOut,
                        const CUtensorMap& mPool, HaloArgs& args, int chunks, cudaStream_t stream) {
     constexpr int B_BLOCK = (BLOCK_N / NCTA) * 128;              // bytes of one (tap, chunk) weight block in ONE CTA
+    constexpr int H_A_STAGE = h_a_stage(H_PITCH);
     const int AUX = (2 * args.c_out + 64) * 4 + (2 * H_MAX_A + 2 * H_MAX_B + 5) * 8 + 16;
     constexpr int MAX_DYN = 232448;
     const int budget = MAX_DYN - 1024 - AUX;
@@ -429,7 +435,7 @@ static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUt
         args.a_stages = st > H_MAX_A ? H_MAX_A : st;
     } else {
         args.b_resident = 0;
-        args.a_stages = (BLOCK_N >= 256) ? 2 : 3;
+        args.a_stages = g_halo_stages > 0 ? g_halo_stages : (BLOCK_N >= 256) ? 2 : 3;
         int avail = budget - args.a_stages * H_A_STAGE;
         if (staging && (avail - staging) / B_BLOCK >= 4) { args.tma_store = 1; avail -= staging; }
         const int sl = avail / B_BLOCK;
@@ -459,12 +465,12 @@ static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUt
     cfg.numAttrs = (NCTA == 2) ? 1 : 0;
     if (args.b_resident) {
         static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true, NCTA>, MAX_DYN, smem_set));
-        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, true, NCTA>, mA0, mA1, mB, mOut, mPool, args));
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, true, NCTA, H_PITCH>, MAX_DYN, smem_set));
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, true, NCTA, H_PITCH>, mA0, mA1, mB, mOut, mPool, args));
     } else {
         static unsigned char smem_set[64] = {0};
-        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false, NCTA>, MAX_DYN, smem_set));
-        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, false, NCTA>, mA0, mA1, mB, mOut, mPool, args));
+        ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_halo_kernel<BLOCK_N, false, NCTA, H_PITCH>, MAX_DYN, smem_set));
+        ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<BLOCK_N, false, NCTA, H_PITCH>, mA0, mA1, mB, mOut, mPool, args));
     }
     ADN_LAUNCH_CHECK();
     return ADN_OK;
@@ -506,9 +512,10 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     args.head_w = head_w; args.head_b = head_b; args.head_out = head_out;
 
     CUtensorMap mA0, mA1, mB;
-    st = make_act_map(&mA0, src0, n, h, w, c0, H_PITCH, H_ROWS);
+    const int pitch = g_halo_pitch;
+    st = make_act_map(&mA0, src0, n, h, w, c0, pitch, H_ROWS);
     if (st != ADN_OK) return st;
-    if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, H_PITCH, H_ROWS); else mA1 = mA0;
+    if (c1 > 0) st = make_act_map(&mA1, src1, n, h1, w1, c1, pitch, H_ROWS); else mA1 = mA0;
     if (st != ADN_OK) return st;
     // CTA pairs (cta_group::2): two pixel tiles per 256-row UMMA, each CTA holding half of the weight rows.  Used where one CTA is
     // bound by the shared-memory operand reads (BLOCK_N 64 / 128: A + B bytes per MMA exceed 128 B/clk), and only when every
@@ -517,7 +524,8 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     // measured (variant B, batch 64): 128-wide layers with >= 2 input chunks gain 8-32 % (upconv3.0: 1 171 -> 1 548 TFLOP/s);
     // 64-wide layers LOSE 30 % in pair mode (a 256x64 UMMA is too short to amortise), so they stay single-CTA; so does the 128-wide
     // layer with ONE input chunk (downconv2.0, K = 576: 0.65 -> 0.89 ms as a pair)
-    const bool pair = g_pair_mode && block_n == 128 && (c0 + c1) >= 128 && args.n_blocks == 1 && num_m >= 2 * (num_sms() / 2);
+    const bool pair = g_pair_mode && num_m >= 2 * (num_sms() / 2) &&
+                      ((block_n == 128 && (c0 + c1) >= 128 && args.n_blocks == 1) || (block_n == 256 && (g_pair_mode & 2)));
     st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), pair ? block_n / 2 : block_n);
     if (st != ADN_OK) return st;
 
@@ -531,18 +539,22 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     }
 
     const int chunks = args.c0_chunks + args.c1_chunks;
+#define ADN_HALO_LAUNCH(BN, NC) (pitch == 10 ? launch_halo<BN, NC, 10>(mA0, mA1, mB, mOut, mPool, args, chunks, stream) \
+                                             : launch_halo<BN, NC, 16>(mA0, mA1, mB, mOut, mPool, args, chunks, stream))
     switch (block_n) {
-        case 256: return launch_halo<256, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
-        case 128: return pair ? launch_halo<128, 2>(mA0, mA1, mB, mOut, mPool, args, chunks, stream)
-                              : launch_halo<128, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
-        default: return launch_halo<64, 1>(mA0, mA1, mB, mOut, mPool, args, chunks, stream);
+        case 256: return pair ? ADN_HALO_LAUNCH(256, 2) : ADN_HALO_LAUNCH(256, 1);
+        case 128: return pair ? ADN_HALO_LAUNCH(128, 2) : ADN_HALO_LAUNCH(128, 1);
+        default: return ADN_HALO_LAUNCH(64, 1);
     }
+#undef ADN_HALO_LAUNCH
 }
 
 }  // namespace adn
 
 // tuning / debugging hook (not in the public header): 0 disables the CTA-pair kernels
 extern "C" void adn__conv_pair_mode(int mode) { adn::g_pair_mode = mode; }
+extern "C" void adn__conv_halo_stages(int stages) { adn::g_halo_stages = stages; }
+extern "C" void adn__conv_halo_pitch(int pitch) { adn::g_halo_pitch = pitch == 16 ? 16 : 10; }
 // 0: conv_halo kernels only; 1 (default state): conv_dx for the 64-output-channel layers, single CTA, epilogue warp sets chosen per
 // layer; 2: conv_dx as CTA pairs; 3 / 4: single CTA with four / two epilogue warp sets forced
 extern "C" void adn__conv_dx_mode(int mode) {

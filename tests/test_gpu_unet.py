@@ -75,7 +75,8 @@ def test_conv3x3_first_layer(n, h, w, relu):
 
 @pytest.mark.parametrize("n,c0,c1,co,h,w", [(2, 64, 0, 64, 20, 19), (1, 64, 0, 128, 37, 26), (2, 128, 0, 256, 9, 6),
                                             (1, 256, 256, 256, 16, 11), (2, 64, 64, 64, 33, 28), (1, 512, 0, 1024, 4, 3),
-                                            (1, 512, 512, 512, 5, 7), (3, 64, 0, 64, 257, 188), (1, 64, 0, 64, 1, 1)])
+                                            (1, 512, 512, 512, 5, 7), (3, 64, 0, 64, 257, 188), (1, 64, 0, 64, 1, 1),
+                                            (2, 128, 0, 256, 64, 157), (2, 128, 128, 512, 50, 163)])   # enough tiles for the CTA-pair kernels (256-wide, 1 and 2 n-blocks)
 def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
     """One implicit-GEMM conv against F.conv2d on the same bf16-rounded operands: only accumulation order and the
     final bf16 store differ, so the bound is tight (output rounding 2^-9 max-wise)."""
@@ -105,6 +106,38 @@ def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
     assert nrel(got, ref) <= 2.5e-3
     if do_pool:
         assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))         # pooling of the stored values is exact
+
+
+@pytest.mark.parametrize("co", [128, 256, 512])
+def test_conv3x3_pair_and_pitch_variants_bit_equal(co):
+    """conv_halo's tuning hooks: CTA pairs off / 128-wide only / 128- and 256-wide (adn__conv_pair_mode 0 / 1 / 3) and the
+    padded 16-pixel halo pitch (adn__conv_halo_pitch) are schedules of the same arithmetic: outputs must be bit-identical."""
+    import ctypes
+    lib = _lib.load(); s = _lib.stream_ptr()
+    for f in (lib.adn__conv_pair_mode, lib.adn__conv_halo_pitch):
+        f.argtypes = [ctypes.c_int]; f.restype = None
+    n, ci, h, w = 2, 128, 66, 157
+    g = torch.Generator().manual_seed(co)
+    x = to_nhwc_bf16(torch.randn(n, ci, h, w, generator=g)).to(dev())
+    wt = (torch.randn(co, ci, 3, 3, generator=g) * (2.0 / (9 * ci)) ** 0.5).to(dev())
+    wp = torch.empty((co, 9, ci), dtype=torch.bfloat16, device=dev())
+    _lib.check(lib.adn_pack_conv3x3_weight_bf16(wt.data_ptr(), co, ci, wp.data_ptr(), s))
+    sc = (0.5 + torch.rand(co, generator=g)).to(dev()); sh = (0.1 * torch.randn(co, generator=g)).to(dev())
+    outs = []
+    try:
+        for pair, pitch in ((0, 10), (1, 10), (3, 10), (3, 16), (0, 16)):
+            lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_pitch(pitch)
+            out = torch.zeros((n, h, w, co), dtype=torch.bfloat16, device=dev())
+            pool = torch.zeros((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=dev())
+            _lib.check(lib.adn_conv3x3_bn_relu_bf16(x.data_ptr(), ci, 0, 0, 0, 0, n, h, w, wp.data_ptr(), co, sc.data_ptr(), sh.data_ptr(),
+                                                    out.data_ptr(), pool.data_ptr(), s))
+            torch.cuda.synchronize()
+            outs.append((out.cpu(), pool.cpu()))
+    finally:
+        lib.adn__conv_pair_mode(3); lib.adn__conv_halo_pitch(10)
+    assert outs[0][0].float().abs().max() > 0
+    for o, p in outs[1:]:
+        assert torch.equal(o, outs[0][0]) and torch.equal(p, outs[0][1])
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
