@@ -414,13 +414,13 @@ def run_b200(args):
             d = per_layer.setdefault(layer, {"ms": 0.0, "flops": 0.0, "n": 0})
             d["ms"] += a.elapsed_time(b); d["flops"] += flops; d["n"] += 1
         tc = {"ms": 0.0, "flops": 0.0, "launches": 0}
-        for kind in ("conv3x3", "conv3x3_head"):
+        for kind in ("conv3x3", "conv3x3_head", "conv3x3_upm"):      # conv3x3_upm counts the MACs it EXECUTES (9 skip + 4 merged taps)
             if kind in agg:
                 for k in tc:
                     tc[k] += agg[kind][k]
         tc_tflops = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
         peak_tc = peaks["bf16_sustained"]
-        roofline = {"kernel": "conv3x3_halo_kernel + conv3x3_dx_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU: 14 + 3 launches/step, the 64-output-channel layers incl. the head-fused one run the kx-in-N variant)", "bound": "tensor",
+        roofline = {"kernel": "conv3x3_halo_kernel + conv3x3_dx_kernel + conv3x3_upm_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU: 12 + 3 + 2 launches/step; the 64-output-channel layers incl. the head-fused one run the kx-in-N variant, the first conv of decoder levels 1-2 runs with the ConvTranspose2d merged into its weights and is counted with the FLOPs it executes)", "bound": "tensor",
                     "achieved": tc_tflops, "peak": peak_tc, "unit": "TFLOP/s", "frac": tc_tflops / peak_tc,
                     "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
                     "launches_per_step": tc["launches"] // reps, "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),

@@ -169,6 +169,22 @@ int adn_conv3x3_bn_relu_head_f32(const void* src0, int c0, const void* src1, int
 int adn_convt2x2_bf16(const void* src, int c_in, int n, int h, int w, const void* w_packed, int c_out,
                       const float* bias, void* out_bf16, void* stream);
 
+/* UpSampleLayer's ConvTranspose2d + F.pad + cat + first Conv3x3 + BN + ReLU (model.py:41-49, :11-13) as ONE implicit GEMM with the
+ * ConvTranspose merged into the conv weights (csrc/conv_upm.cu): skip (n,h,w,c0) and low (n,hl,wl,cl) NHWC bf16 -> out (n,h,w,c_out),
+ * h - 2*hl and w - 2*wl in {0,1} (F.pad puts the missing row / column at the end), c0, cl multiples of 64, c_out a multiple of 128.
+ * w_merged / shift_m / wb come from adn_pack_upmerged_weight_bf16.  Eval mode only (the training step keeps the two layers apart). */
+int adn_conv3x3_upmerged_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
+                                      const void* w_merged, int c_out, const float* scale, const float* shift_m, const float* wb,
+                                      void* out_bf16, void* stream);
+
+/* Checkpoint-load-time merge for the entry above.  w3: the level's first conv weight (c_out, c0 + cup, 3, 3) f32 (input channels
+ * [skip, up], model.py:49); wt / bt: ConvTranspose2d weight (cl, cup, 2, 2) and bias (cup) f32; scale / shift: the folded BatchNorm of
+ * the conv (adn_fold_bn_f32).  Writes w_merged bf16 [c_out][9*c0 + 16*cl] (skip taps, then per parity class and 2x2 tap the product
+ * of the conv and ConvTranspose weights, summed in fp32), shift_m (c_out) = shift + the interior ConvTranspose-bias term, and
+ * wb (9, c_out) = the per-tap bias terms the kernel takes back out on border pixels. */
+int adn_pack_upmerged_weight_bf16(const float* w3, const float* wt, const float* bt, const float* scale, const float* shift,
+                                  int c_out, int c0, int cup, int cl, void* w_merged, float* shift_m, float* wb, void* stream);
+
 /* MaxPool2d(2) on NHWC bf16 (model.py:26,31), floor semantics: (n,h,w,c) -> (n,h/2,w/2,c). */
 int adn_maxpool2x2_bf16(const void* src, int n, int h, int w, int c, void* out, void* stream);
 

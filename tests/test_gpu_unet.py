@@ -185,6 +185,54 @@ def test_conv3x3_64_output_channels_all_kernels(mode, n, c0, c1, h, w, relu):
         assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))
 
 
+@pytest.mark.parametrize("exact_weights", [True, False])
+@pytest.mark.parametrize("n,c0,cl,co,hl,wl,h,w", [(2, 64, 128, 128, 8, 9, 17, 18), (1, 128, 256, 256, 5, 20, 10, 41), (3, 64, 128, 512, 17, 9, 35, 18),
+                                                  (2, 128, 128, 128, 1, 1, 2, 2), (4, 64, 64, 256, 33, 70, 66, 141)])
+def test_conv3x3_upmerged_matches_convtranspose_pad_cat_conv(n, c0, cl, co, hl, wl, h, w, exact_weights):
+    """UpSampleLayer.forward (model.py:41-50) up to the first ReLU -- ConvTranspose2d(k=2,s=2) + bias, F.pad to the skip's size,
+    cat([skip, up]), Conv3x3 + folded BN + ReLU -- against the merged-weight kernel (csrc/conv_upm.cu), which never forms `up`.
+    exact_weights: conv / ConvTranspose weights are small integers times a power of two, so the merged products are exact in
+    bf16 and only accumulation order and the final bf16 store differ (tight bound, also proves the border-bias correction);
+    otherwise the merged weights carry one bf16 rounding of their own (the two-layer path rounds `up` instead)."""
+    lib = _lib.load(); s = _lib.stream_ptr()
+    cup = cl // 2
+    g = torch.Generator().manual_seed(h * 100 + w + co)
+    skip = bf16_round(torch.randn(n, c0, h, w, generator=g))
+    low = bf16_round(torch.randn(n, cl, hl, wl, generator=g))
+    if exact_weights:
+        w3 = torch.randint(-1, 2, (co, c0 + cup, 3, 3), generator=g).float() * 2.0 ** -5
+        wt = torch.randint(-1, 2, (cl, cup, 2, 2), generator=g).float() * (torch.rand(cl, cup, 2, 2, generator=g) < 0.25).float() * 0.25
+    else:
+        w3 = torch.randn(co, c0 + cup, 3, 3, generator=g) * (2.0 / (9 * (c0 + cup))) ** 0.5
+        wt = torch.randn(cl, cup, 2, 2, generator=g) * (1.0 / cl) ** 0.5
+    bt = torch.randn(cup, generator=g) * 0.5
+    scale = 0.5 + torch.rand(co, generator=g); shift = 0.1 * torch.randn(co, generator=g)
+    up = F.conv_transpose2d(low.double(), wt.double(), bt.double(), stride=2)
+    up = F.pad(up, [0, w - 2 * wl, 0, h - 2 * hl])
+    w3r = w3 if exact_weights else torch.cat([bf16_round(w3[:, :c0]), w3[:, c0:]], 1)      # the skip half is rounded like any conv weight
+    ref = F.relu(F.conv2d(torch.cat([skip.double(), up], 1), w3r.double(), padding=1) * scale.double().view(1, -1, 1, 1)
+                 + shift.double().view(1, -1, 1, 1)).float()
+    d = dev()
+    wm = torch.empty((co, 9 * c0 + 16 * cl), dtype=torch.bfloat16, device=d)
+    shift_m = torch.empty(co, device=d); wb = torch.empty((9, co), device=d)
+    w3d, wtd, btd, sc, sh = (t.to(d).contiguous() for t in (w3, wt, bt, scale, shift))
+    _lib.check(lib.adn_pack_upmerged_weight_bf16(w3d.data_ptr(), wtd.data_ptr(), btd.data_ptr(), sc.data_ptr(), sh.data_ptr(), co, c0, cup, cl,
+                                                 wm.data_ptr(), shift_m.data_ptr(), wb.data_ptr(), s))
+    a0 = to_nhwc_bf16(skip).to(d); a1 = to_nhwc_bf16(low).to(d)
+    out = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=d)
+    _lib.check(lib.adn_conv3x3_upmerged_bn_relu_bf16(a0.data_ptr(), c0, a1.data_ptr(), cl, hl, wl, n, h, w, wm.data_ptr(), co,
+                                                     sc.data_ptr(), shift_m.data_ptr(), wb.data_ptr(), out.data_ptr(), s))
+    torch.cuda.synchronize()
+    got = from_nhwc(out.cpu())
+    assert torch.isfinite(got).all()
+    if exact_weights:
+        assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+        assert nrel(got, ref) <= 2.5e-3
+    else:
+        assert float((got - ref).abs().max()) <= 1.2e-2 * float(ref.abs().max())
+        assert nrel(got, ref) <= 4e-3
+
+
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
 def test_convt2x2(n, ci, co, h, w):
     lib = _lib.load(); s = _lib.stream_ptr()
