@@ -413,6 +413,10 @@ static int g_dx_mode = 1;        // 0: never use the kx-in-N kernel of conv_dx.c
 static int g_pair_mode = 3;      // 0: never use CTA pairs; 1: where the layer is shared-memory-operand bound and a pair pays off; 3: also the 256-wide layers
 static int g_halo_pitch = 10;    // 10: dense halo tile; 16: padded rows
 static int g_halo_stages = 0;    // > 0: A stages of the streaming-B configuration (tuning hook)
+// tuning hook bits: 1 = CTA pairs also for the one-chunk 128-wide layer (measured: downconv2.0 0.63 -> 0.87 ms, off);
+// 2 = stream the weights when keeping them resident would cost the TMA-store epilogue its staging buffers (measured at batch 64:
+// downconv2.3 1.15 -> 1.02 ms, downconv2.0 0.63 -> 0.60, upconv3.3 0.92 -> 0.90; on)
+static int g_halo_tune = 2;
 
 template <int BLOCK_N, int NCTA, int H_PITCH>
 static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUtensorMap& mB, const CUtensorMap& mOut,
@@ -426,7 +430,9 @@ static int launch_halo(const CUtensorMap& mA0, const CUtensorMap& mA1, const CUt
     // TMA-store staging is worth its shared memory only where it does not starve the operand rings
     const int staging = (args.epi == HEPI_NHWC) ? 2 * H_OUT_STAGE + (args.pool_out ? 2 * H_POOL_STAGE : 0) : 0;
     args.tma_store = 0;
-    if (args.n_blocks == 1 && total_b + 2 * H_A_STAGE <= budget) {
+    bool resident = args.n_blocks == 1 && total_b + 2 * H_A_STAGE <= budget;
+    if (resident && (g_halo_tune & 2) && staging && (budget - total_b) - staging < 3 * H_A_STAGE) resident = false;
+    if (resident) {
         args.b_resident = 1;
         args.b_slots = 9 * chunks;
         int avail = budget - total_b;
@@ -525,7 +531,7 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
     // 64-wide layers LOSE 30 % in pair mode (a 256x64 UMMA is too short to amortise), so they stay single-CTA; so does the 128-wide
     // layer with ONE input chunk (downconv2.0, K = 576: 0.65 -> 0.89 ms as a pair)
     const bool pair = g_pair_mode && num_m >= 2 * (num_sms() / 2) &&
-                      ((block_n == 128 && (c0 + c1) >= 128 && args.n_blocks == 1) || (block_n == 256 && (g_pair_mode & 2)));
+                      ((block_n == 128 && ((c0 + c1) >= 128 || (g_halo_tune & 1)) && args.n_blocks == 1) || (block_n == 256 && (g_pair_mode & 2)));
     st = make_weight_map(&mB, w_packed, c_out, 9 * (c0 + c1), pair ? block_n / 2 : block_n);
     if (st != ADN_OK) return st;
 
@@ -553,6 +559,7 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
 
 // tuning / debugging hook (not in the public header): 0 disables the CTA-pair kernels
 extern "C" void adn__conv_pair_mode(int mode) { adn::g_pair_mode = mode; }
+extern "C" void adn__conv_halo_tune(int bits) { adn::g_halo_tune = bits; }
 extern "C" void adn__conv_halo_stages(int stages) { adn::g_halo_stages = stages; }
 extern "C" void adn__conv_halo_pitch(int pitch) { adn::g_halo_pitch = pitch == 16 ? 16 : 10; }
 // 0: conv_halo kernels only; 1 (default state): conv_dx for the 64-output-channel layers, single CTA, epilogue warp sets chosen per

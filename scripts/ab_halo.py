@@ -13,18 +13,18 @@ from audiodenoiser_b200.model import UNet
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 lib = _lib.load()
-for f in (lib.adn__conv_halo_pitch, lib.adn__conv_pair_mode, lib.adn__conv_halo_stages):
+for f in (lib.adn__conv_halo_pitch, lib.adn__conv_pair_mode, lib.adn__conv_halo_stages, lib.adn__conv_halo_tune):
     f.argtypes = [ctypes.c_int]; f.restype = None
 net = UNet().eval()
 net.load_state_dict(seeded_state_dict(3))
 x = torch.rand(batch, 1, 257, 1034, device="cuda")
-MODES = {"pitch16": (16, 1, 0), "p10+pair256": (10, 3, 0), "p10+pair256+3st": (10, 3, 3), "p10+pair256+4st": (10, 3, 4)}
+MODES = {"pitch16,pair128,resident": (16, 1, 0, 0), "pitch10": (10, 1, 0, 0), "+pair256": (10, 3, 0, 0), "+stream-for-tma-store (default)": (10, 3, 0, 2)}
 res = {m: {} for m in MODES}
 outs = {}
 with torch.no_grad():
     for rep in range(6):
-        for mode, (pitch, pair, stages) in MODES.items():
-            lib.adn__conv_halo_pitch(pitch); lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_stages(stages)
+        for mode, (pitch, pair, stages, tune) in MODES.items():
+            lib.adn__conv_halo_pitch(pitch); lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_stages(stages); lib.adn__conv_halo_tune(tune)
             net.profile = []
             y = net(x)
             torch.cuda.synchronize()

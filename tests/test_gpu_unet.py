@@ -110,11 +110,11 @@ def test_conv3x3_bn_relu(n, c0, c1, co, h, w):
 
 @pytest.mark.parametrize("co", [128, 256, 512])
 def test_conv3x3_pair_and_pitch_variants_bit_equal(co):
-    """conv_halo's tuning hooks: CTA pairs off / 128-wide only / 128- and 256-wide (adn__conv_pair_mode 0 / 1 / 3) and the
-    padded 16-pixel halo pitch (adn__conv_halo_pitch) are schedules of the same arithmetic: outputs must be bit-identical."""
+    """conv_halo's tuning hooks: CTA pairs off / 128-wide only / 128- and 256-wide (adn__conv_pair_mode 0 / 1 / 3), the
+    padded 16-pixel halo pitch (adn__conv_halo_pitch) and the resident / streamed weight choice (adn__conv_halo_tune) are schedules of the same arithmetic: outputs must be bit-identical."""
     import ctypes
     lib = _lib.load(); s = _lib.stream_ptr()
-    for f in (lib.adn__conv_pair_mode, lib.adn__conv_halo_pitch):
+    for f in (lib.adn__conv_pair_mode, lib.adn__conv_halo_pitch, lib.adn__conv_halo_tune):
         f.argtypes = [ctypes.c_int]; f.restype = None
     n, ci, h, w = 2, 128, 66, 157
     g = torch.Generator().manual_seed(co)
@@ -125,8 +125,8 @@ def test_conv3x3_pair_and_pitch_variants_bit_equal(co):
     sc = (0.5 + torch.rand(co, generator=g)).to(dev()); sh = (0.1 * torch.randn(co, generator=g)).to(dev())
     outs = []
     try:
-        for pair, pitch in ((0, 10), (1, 10), (3, 10), (3, 16), (0, 16)):
-            lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_pitch(pitch)
+        for pair, pitch, tune in ((0, 10, 2), (1, 10, 2), (3, 10, 2), (3, 16, 0), (0, 16, 0), (3, 10, 0), (1, 10, 1)):
+            lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_pitch(pitch); lib.adn__conv_halo_tune(tune)
             out = torch.zeros((n, h, w, co), dtype=torch.bfloat16, device=dev())
             pool = torch.zeros((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=dev())
             _lib.check(lib.adn_conv3x3_bn_relu_bf16(x.data_ptr(), ci, 0, 0, 0, 0, n, h, w, wp.data_ptr(), co, sc.data_ptr(), sh.data_ptr(),
@@ -134,7 +134,7 @@ def test_conv3x3_pair_and_pitch_variants_bit_equal(co):
             torch.cuda.synchronize()
             outs.append((out.cpu(), pool.cpu()))
     finally:
-        lib.adn__conv_pair_mode(3); lib.adn__conv_halo_pitch(10)
+        lib.adn__conv_pair_mode(3); lib.adn__conv_halo_pitch(10); lib.adn__conv_halo_tune(2)
     assert outs[0][0].float().abs().max() > 0
     for o, p in outs[1:]:
         assert torch.equal(o, outs[0][0]) and torch.equal(p, outs[0][1])
