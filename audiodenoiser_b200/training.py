@@ -87,6 +87,7 @@ class TrainEngine:
         self.zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.ws = torch.empty(int(self.lib.adn_train_workspace_bytes()), dtype=torch.uint8, device=dev)
         self.wg_ws = torch.empty(int(self.lib.adn_wgrad_workspace_bytes()), dtype=torch.uint8, device=dev)
+        self.wg_ws2 = None                       # second split-K workspace: weight gradients alternate between two side streams
         self.norm_coef = torch.zeros(2, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=dev)      # AdamW step count, advanced on the device
         self._graph = None
@@ -283,10 +284,23 @@ class TrainEngine:
         wsp = self.ws.data_ptr()
         main = torch.cuda.current_stream(self.device)
         if self._wg_stream is None:
-            self._wg_stream = torch.cuda.Stream(self.device)
-        side = self._wg_stream if self.overlap_wgrad else main
-        ss = side.cuda_stream
-        keep = []                              # tensors the side stream still reads: alive until it has been joined
+            self._wg_stream = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            self.wg_ws2 = torch.empty_like(self.wg_ws)
+        n_side = int(os.environ.get("ADN_WGRAD_STREAMS", "2")) if self.overlap_wgrad else 0
+        sides = [main] if n_side == 0 else list(self._wg_stream[:n_side])
+        wss = [self.wg_ws, self.wg_ws2]
+        turn = [0]
+
+        def next_side():                       # weight gradients alternate between the side streams, each with its own split-K workspace
+            k = turn[0] % len(sides)
+            turn[0] += 1
+            return sides[k], wss[k].data_ptr()
+
+        def join_sides():
+            for sd in sides:
+                main.wait_stream(sd)
+
+        keep = []                              # tensors the side streams still read: alive until they have been joined
 
         def conv_bwd(layer, dy_ptr, dy_ld, need_dx=True):
             p, ci_, bi, l, c0, c1, co = layer
@@ -308,14 +322,18 @@ class TrainEngine:
             # The weight gradient only needs dz and the saved input; nothing downstream reads it before the optimizer.  It runs on a
             # SIDE STREAM (a parallel branch of the captured graph), beside the data-gradient chain of the following layers: the deep
             # layers' kernels fill a fraction of the SMs each, so the two branches overlap instead of queueing.
-            side.wait_stream(main)
             keep.append(dz)
+            side, wg = next_side()
+            side.wait_stream(main)
             with torch.cuda.stream(side):
-                _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src0.data_ptr(), c0, hh, ww, n, hh, ww, self._gptr(wkey), 0, c0 + c1, self.wg_ws.data_ptr(), ss), f"wgrad {wkey}")
+                _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src0.data_ptr(), c0, hh, ww, n, hh, ww, self._gptr(wkey), 0, c0 + c1, wg, side.cuda_stream), f"wgrad {wkey}")
+            self.launch_count += 3
+            if c1:
+                side, wg = next_side()
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src1.data_ptr(), c1, hh, ww, n, hh, ww, self._gptr(wkey), c0, c0 + c1, wg, side.cuda_stream), f"wgrad {wkey}")
                 self.launch_count += 3
-                if c1:
-                    _lib.check(lib.adn_conv3x3_wgrad_f32(dz.data_ptr(), co, src1.data_ptr(), c1, hh, ww, n, hh, ww, self._gptr(wkey), c0, c0 + c1, self.wg_ws.data_ptr(), ss), f"wgrad {wkey}")
-                    self.launch_count += 3
             if not need_dx:
                 return None
             dx = torch.empty((n, hh, ww, c0 + c1), **bf)
@@ -348,10 +366,11 @@ class TrainEngine:
                 ci = _CH[l + 1]
                 up_ptr = d_cat.data_ptr() + 2 * c
                 _lib.check(lib.adn_channel_sum_f32(up_ptr, 2 * c, n * hs[l] * wz[l], c, self._gptr(f"{name}.bias"), wsp, s), "convT bias grad")
+                side, wg = next_side()
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
                     _lib.check(lib.adn_convt2x2_wgrad_f32(src.data_ptr(), ci, d_cat.data_ptr(), 2 * c, c, c, n, hs[l + 1], wz[l + 1],
-                                                          self._gptr(f"{name}.weight"), self.wg_ws.data_ptr(), ss), "convT wgrad")
+                                                          self._gptr(f"{name}.weight"), wg, side.cuda_stream), "convT wgrad")
                 d_src = torch.empty((n, hs[l + 1], wz[l + 1], ci), **bf)
                 _lib.check(lib.adn_convt2x2_dgrad_bf16(d_cat.data_ptr(), 2 * c, c, c, n, hs[l + 1], wz[l + 1], self.packed[name][1].data_ptr(), ci,
                                                        d_src.data_ptr(), s), "convT dgrad")
@@ -359,12 +378,12 @@ class TrainEngine:
                 cur_dy, cur_ld = d_src, ci
             # DDP: the decoder's gradients (flat slice from upconv1.up.weight to the end, 39 % of the parameters) are final: their
             # all-reduce runs under the bottleneck / encoder backward
-            main.wait_stream(side)
+            join_sides()
             self._start_bucket(self.offsets["upconv1.up.weight"][0], self.numel)
             # bottleneck
             d_a = conv_bwd(layers[9], cur_dy.data_ptr(), cur_ld)
             d_pool = conv_bwd(layers[8], d_a.data_ptr(), 1024)
-            main.wait_stream(side)
+            join_sides()
             self._start_bucket(self.offsets["bottleneck.double_conv.0.weight"][0], self.offsets["upconv1.up.weight"][0])   # 46 %
             # encoder, levels 3..0
             for l in (3, 2, 1, 0):
@@ -376,7 +395,7 @@ class TrainEngine:
                 self.launch_count += 1
                 d_a = conv_bwd(layers[2 * l + 1], dy_s.data_ptr(), c)
                 d_pool = conv_bwd(layers[2 * l], d_a.data_ptr(), c, need_dx=(l > 0))
-            main.wait_stream(side)
+            join_sides()
             keep.clear()
             self._start_bucket(0, self.offsets["bottleneck.double_conv.0.weight"][0])                                    # 15 %
         self.saved = None
