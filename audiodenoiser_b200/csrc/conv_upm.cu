@@ -330,6 +330,371 @@ conv3x3_upm_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant__
     if (warp == 2) tmem_dealloc_pair(tmem_own, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ two parity classes per tile
+// The kernel above reads all four skip planes for every parity class: 78 KB of TMA writes per 64-channel chunk and class.  With a
+// 256-wide accumulator that is hidden; with CO = 128 output channels (decoder level of 128 channels) the 256x128x16 UMMAs are too
+// short (measured 2.36 ms against 2.03 for ConvTranspose + conv).  conv3x3_upm2_kernel therefore computes BOTH column-parity classes
+// (py, 0) and (py, 1) of a tile in one 256-column accumulator [class 0 | class 1]:
+//   * every A view that both classes read (the un-shifted column of a plane, the middle column of the low tile) is ONE N = 256 UMMA
+//     whose B block stacks the two classes' weights; the views only one class reads are N = 128 UMMAs into that class's half;
+//   * the planes are loaded once for two classes, so the TMA writes per UMMA cycle drop from 66 to 48 B/clk and the mean
+//     operand read from 96 to 75 B/clk.
+// B comes from two packed tensors: Bsh [2*CO][..] (shared views) and B1 [CO][..] (single views), blocks in consumption order.
+constexpr int U2_LOW_BW = U_TW + 2;                               // the low tile spans columns x0-1 .. x0+8 for the two classes
+constexpr int U2_A_STAGE = ((U_BH * U2_LOW_BW * 128) + 1023) & ~1023;   // 22 528 B (skip plane boxes are 17 x 9)
+constexpr int U2_B_SLOT = 128 * 128;                              // one CTA's half of a shared block (a single block uses half of it)
+
+struct Upm2Args {
+    int c0_chunks, cl_chunks;
+    int n_img, H, W, Hu, Wu;
+    int tiles_y, ntx, pair_img, work_total;
+    FastDiv div_ntx, div_ty;
+    int a_stages, b_slots;
+    const float* scale;
+    const float* shift;
+    const float* wb;
+};
+
+template <int CO>
+__global__ void __launch_bounds__(U_THREADS, 1)
+conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant__ CUtensorMap tmLow,
+                    const __grid_constant__ CUtensorMap tmBsh, const __grid_constant__ CUtensorMap tmB1, const Upm2Args a) {
+    constexpr int BLOCK_N = 2 * CO;
+    static_assert(BLOCK_N == 256, "two classes of 128 output channels");
+    constexpr int TMEM_COLS = 2 * BLOCK_N;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = (cta_rank == 0);
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
+
+    const uint32_t a_base = smem_base;
+    const uint32_t b_base = a_base + (uint32_t)a.a_stages * U2_A_STAGE;
+    const uint32_t stage_off = (uint32_t)a.a_stages * U2_A_STAGE + (uint32_t)a.b_slots * U2_B_SLOT;
+    const uint32_t aux_off = stage_off + 2u * U_OUT_STAGE;
+    float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
+    float* s_shift = s_scale + CO;
+    const uint32_t aux_f32 = (uint32_t)(2 * CO) * 4;
+    const uint32_t bar_base = smem_base + aux_off + aux_f32;
+    auto full_a = [&](int s) { return bar_base + 8u * s; };
+    auto empty_a = [&](int s) { return bar_base + 8u * (U_MAX_A + s); };
+    auto full_b = [&](int s) { return bar_base + 8u * (2 * U_MAX_A + s); };
+    auto empty_b = [&](int s) { return bar_base + 8u * (2 * U_MAX_A + U_MAX_B + s); };
+    auto tfull = [&](int s) { return bar_base + 8u * (2 * U_MAX_A + 2 * U_MAX_B + s); };
+    auto tempty = [&](int s) { return bar_base + 8u * (2 * U_MAX_A + 2 * U_MAX_B + 2 + s); };
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem_gen + aux_off + aux_f32 + (2 * U_MAX_A + 2 * U_MAX_B + 4) * 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < 4; ++p) { tma_prefetch_desc(&maps.skip[p]); tma_prefetch_desc(&maps.out[p]); }
+        tma_prefetch_desc(&tmLow); tma_prefetch_desc(&tmBsh); tma_prefetch_desc(&tmB1);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < U_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < U_MAX_B; ++s) { mbar_init(full_b(s), 1); mbar_init(empty_b(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), 2 * U_EPI_THREADS / 32); }
+        fence_barrier_init();
+    }
+    if (warp == 2) { tmem_alloc_pair(smem_u32(tmem_ptr_smem), TMEM_COLS); tmem_relinquish_pair(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_own = *tmem_ptr_smem;
+    const uint32_t tmem_base = ld_shared_cluster_u32(mapa_shared(smem_u32(tmem_ptr_smem), 0));
+
+    const int work_first = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
+    const int Hc0 = (a.H + 1) >> 1, Hc1 = a.H >> 1, Wc0 = (a.W + 1) >> 1;
+
+    struct Tile { int py, ty, tx, img; bool live; };
+    auto decode = [&](int w) {
+        Tile t;
+        t.py = w & 1;
+        const int q = w >> 1;
+        const int r = fast_div(q, a.div_ntx);
+        const int txq = q - r * a.ntx;
+        const int aa = fast_div(r, a.div_ty);
+        t.ty = r - aa * a.tiles_y;
+        t.tx = a.pair_img ? txq : 2 * txq + (int)cta_rank;
+        t.img = a.pair_img ? 2 * aa + (int)cta_rank : aa;
+        const int tx0 = a.pair_img ? txq : 2 * txq;
+        t.live = (t.ty * U_TH < (t.py ? Hc1 : Hc0)) && (tx0 * U_TW < Wc0);
+        return t;
+    };
+    auto full_a_sig = [&](int s) { return mapa_shared(full_a(s), 0); };
+    auto full_b_sig = [&](int s) { return mapa_shared(full_b(s), 0); };
+    const int NS = a.c0_chunks * 8 + a.cl_chunks * 2;              // 64-wide K blocks per row parity in Bsh / B1
+    const int N1 = a.c0_chunks * 8 + a.cl_chunks * 4;
+
+    if (warp == 0) {
+        // ===================================================================== A producer
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            auto load = [&](const CUtensorMap* map, uint32_t bytes, int c, int x, int y, int img) {
+                mbar_wait(empty_a(stage), phase ^ 1u);
+                if (leader) mbar_arrive_expect_tx(full_a(stage), 2 * bytes);
+                tma_load_4d_pair(a_base + (uint32_t)stage * U2_A_STAGE, map, full_a_sig(stage), c, x, y, img);
+                if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+            };
+            for (int w = work_first; w < a.work_total; w += work_step) {
+                const Tile t = decode(w);
+                if (!t.live) continue;
+                const int x0 = t.tx * U_TW, y0 = t.ty * U_TH;
+                for (int ch = 0; ch < a.c0_chunks; ++ch)
+                    for (int plane = 0; plane < 4; ++plane) {
+                        const int qy = plane >> 1, qx = plane & 1;
+                        const int oy = (qy != t.py && t.py == 0) ? -1 : 0;
+                        load(&maps.skip[plane], U_A_BYTES, ch * 64, x0 - qx, y0 + oy, t.img);      // odd plane: columns x0-1 .. x0+7
+                    }
+                for (int ch = 0; ch < a.cl_chunks; ++ch)
+                    load(&tmLow, U_BH * U2_LOW_BW * 128, ch * 64, x0 - 1, y0 - (1 - t.py), t.img);
+            }
+        }
+    } else if (warp == 2) {
+        // ===================================================================== B producer
+        if (lane == 0) {
+            int slot = 0; uint32_t phase = 0;
+            auto load_sh = [&](int kb) {
+                mbar_wait(empty_b(slot), phase ^ 1u);
+                if (leader) mbar_arrive_expect_tx(full_b(slot), 2 * 128 * 128);
+                tma_load_2d_pair(b_base + (uint32_t)slot * U2_B_SLOT, &tmBsh, full_b_sig(slot), kb * 64, (int)cta_rank * 128);
+                if (++slot == a.b_slots) { slot = 0; phase ^= 1u; }
+            };
+            auto load_1 = [&](int kb) {
+                mbar_wait(empty_b(slot), phase ^ 1u);
+                if (leader) mbar_arrive_expect_tx(full_b(slot), 2 * 64 * 128);
+                tma_load_2d_pair(b_base + (uint32_t)slot * U2_B_SLOT, &tmB1, full_b_sig(slot), kb * 64, (int)cta_rank * 64);
+                if (++slot == a.b_slots) { slot = 0; phase ^= 1u; }
+            };
+            for (int w = work_first; w < a.work_total; w += work_step) {
+                const Tile t = decode(w);
+                if (!t.live) continue;
+                for (int ch = 0; ch < a.c0_chunks; ++ch)
+                    for (int plane = 0; plane < 4; ++plane) {
+                        const int nky = ((plane >> 1) != t.py) ? 2 : 1;
+                        for (int iy = 0; iy < nky; ++iy) {
+                            const int idx = (ch * 4 + plane) * 2 + iy;
+                            load_sh(t.py * NS + idx);
+                            load_1(t.py * N1 + idx);
+                        }
+                    }
+                for (int ch = 0; ch < a.cl_chunks; ++ch)
+                    for (int dy = 0; dy < 2; ++dy) {
+                        load_sh(t.py * NS + a.c0_chunks * 8 + ch * 2 + dy);
+                        load_1(t.py * N1 + a.c0_chunks * 8 + (ch * 2 + dy) * 2);
+                        load_1(t.py * N1 + a.c0_chunks * 8 + (ch * 2 + dy) * 2 + 1);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (leader) {
+            constexpr uint32_t idesc_sh = make_idesc(BLOCK_N, 256), idesc_1 = make_idesc(CO, 256);
+            constexpr uint64_t B_STEP = (uint64_t)(U2_B_SLOT >> 4);
+            int sa = 0; uint32_t pa = 0;
+            int sb = 0; uint32_t pb = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            const uint64_t db_base = make_sw128_desc(b_base);
+            // one B slot: four k-steps of a UMMA with `idesc` into accumulator columns d, A view at `da`
+            auto issue = [&](uint32_t d, uint64_t da, uint32_t idesc, uint32_t first_acc, bool release_a, int a_stage) {
+                mbar_wait(full_b(sb), pb);
+                tc_fence_after();
+                const uint64_t db = db_base + (uint64_t)sb * B_STEP;
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_pair(d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (k != 0) ? 1u : first_acc);
+                    umma_commit_pair(empty_b(sb));
+                    if (release_a) umma_commit_pair(empty_a(a_stage));
+                }
+                __syncwarp();
+                if (++sb == a.b_slots) { sb = 0; pb ^= 1u; }
+            };
+            for (int w = work_first; w < a.work_total; w += work_step) {
+                const Tile t = decode(w);
+                if (!t.live) continue;
+                mbar_wait(tempty(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                uint32_t started = 0;
+                for (int u = 0; u < a.c0_chunks * 4; ++u) {
+                    const int plane = u & 3, qx = plane & 1;
+                    const int nky = ((plane >> 1) != t.py) ? 2 : 1;
+                    mbar_wait(full_a(sa), pa);
+                    tc_fence_after();
+                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * U2_A_STAGE, U_BW * 128);
+                    for (int iy = 0; iy < nky; ++iy) {
+                        // shared view: box column qx (both classes); single view: box column 1 - qx, class 1 - qx only
+                        issue(d_tmem, da_stage + (uint64_t)((iy * U_BW + qx) * 8), idesc_sh, started, false, sa);
+                        started = 1u;
+                        issue(d_tmem + (uint32_t)((1 - qx) * CO), da_stage + (uint64_t)((iy * U_BW + (1 - qx)) * 8), idesc_1, 1u, iy == nky - 1, sa);
+                    }
+                    if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
+                }
+                for (int ch = 0; ch < a.cl_chunks; ++ch) {
+                    mbar_wait(full_a(sa), pa);
+                    tc_fence_after();
+                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * U2_A_STAGE, U2_LOW_BW * 128);
+                    for (int dy = 0; dy < 2; ++dy) {
+                        issue(d_tmem, da_stage + (uint64_t)((dy * U2_LOW_BW + 1) * 8), idesc_sh, 1u, false, sa);
+                        issue(d_tmem, da_stage + (uint64_t)((dy * U2_LOW_BW + 0) * 8), idesc_1, 1u, false, sa);
+                        issue(d_tmem + (uint32_t)CO, da_stage + (uint64_t)((dy * U2_LOW_BW + 2) * 8), idesc_1, 1u, dy == 1, sa);
+                    }
+                    if (++sa == a.a_stages) { sa = 0; pa ^= 1u; }
+                }
+                if (elect_one()) umma_commit_pair(tfull(acc));
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===================================================================== epilogue
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int et = threadIdx.x - 96;
+        const int lx = row & (U_TW - 1), ly = row >> 3;
+        for (int c = et; c < CO; c += U_EPI_THREADS) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
+        named_bar_sync(1, U_EPI_THREADS);
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t store_groups = 0;
+        const uint32_t tempty_sig0 = mapa_shared(tempty(0), 0), tempty_sig1 = mapa_shared(tempty(1), 0);
+        for (int w = work_first; w < a.work_total; w += work_step) {
+            const Tile t = decode(w);
+            if (!t.live) continue;
+            const int Y = 2 * (t.ty * U_TH + ly) + t.py;
+            uint32_t emask2[2] = {0u, 0u};
+            if (Y < a.H && t.img < a.n_img) {
+                uint32_t ry = 0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) if (Y + k - 1 < 0 || Y + k - 1 >= a.Hu) ry |= 1u << k;
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    const int X = 2 * (t.tx * U_TW + lx) + px;
+                    if (X >= a.W) continue;
+                    uint32_t rx = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) if (X + k - 1 < 0 || X + k - 1 >= a.Wu) rx |= 1u << k;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            if (((ry >> ky) | (rx >> kx)) & 1u) emask2[px] |= 1u << (ky * 3 + kx);
+                }
+            }
+            mbar_wait(tfull(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            auto group = [&](const int c0, const bool first_half, const uint32_t (&r)[32]) {
+                const int px = c0 / CO, cc = c0 - px * CO;                     // class and channel offset of this 32-column group
+                const uint32_t emask = px ? emask2[1] : emask2[0];
+                const float4* sc4 = reinterpret_cast<const float4*>(s_scale + cc);
+                const float4* sh4 = reinterpret_cast<const float4*>(s_shift + cc);
+                float2 yv[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 sc = sc4[i], sh = sh4[i];
+                    yv[2 * i] = pk_fma(make_float2(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])), make_float2(sc.x, sc.y), make_float2(sh.x, sh.y));
+                    yv[2 * i + 1] = pk_fma(make_float2(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])), make_float2(sc.z, sc.w), make_float2(sh.z, sh.w));
+                }
+                if (emask) {
+                    const float* wb = a.wb + cc;
+                    for (int tap = 0; tap < 9; ++tap)
+                        if ((emask >> tap) & 1u) {
+                            const float2* w2 = reinterpret_cast<const float2*>(wb + tap * CO);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { const float2 v = w2[i]; yv[i].x -= v.x; yv[i].y -= v.y; }
+                        }
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[i] = pack_relu_bf16x2(yv[i].x, yv[i].y);
+                const uint32_t cbase = first_half ? 0u : 4u;
+                const uint32_t buf = store_groups & 1u;
+                const uint32_t o_stage = smem_base + stage_off + buf * U_OUT_STAGE;
+                if (first_half) {
+                    if (et == 0) bulk_wait_read<1>();
+                    named_bar_sync(1, U_EPI_THREADS);
+                }
+                const uint32_t rbase = o_stage + (uint32_t)row * 128u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    st_shared_v4(rbase + (((cbase + i) ^ ((uint32_t)row & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+                if (!first_half) {
+                    fence_proxy_async();
+                    named_bar_sync(1, U_EPI_THREADS);
+                    if (et == 0) {
+                        tma_store_4d(&maps.out[t.py * 2 + px], o_stage, cc - 32, t.tx * U_TW, t.ty * U_TH, t.img);
+                        bulk_commit();
+                    }
+                    ++store_groups;
+                }
+            };
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t_row, r0);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+                tmem_ld_wait();
+                tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
+                group(c0, true, r0);
+                tmem_ld_wait();
+                if (c0 + 64 < BLOCK_N) tmem_ld32(t_row + (uint32_t)(c0 + 64), r0);
+                group(c0 + 32, false, r1);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_sig1 : tempty_sig0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (et == 0) bulk_wait<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    if (warp == 2) tmem_dealloc_pair(tmem_own, TMEM_COLS);
+}
+
+// Bsh / B1 for conv3x3_upm2_kernel, gathered from the merged tensor of the one-class kernel (wm: [co][9*c0 + 16*cl], see below).
+// Block order per row parity py: skip (chunk, plane, iy in {0,1}), then low (chunk, dy) [B1: (chunk, dy, s)].  Unused iy slots are zero.
+__global__ void upm2_repack_kernel(const __nv_bfloat16* __restrict__ wm, int co_n, int c0, int cl, __nv_bfloat16* __restrict__ bsh,
+                                   __nv_bfloat16* __restrict__ b1) {
+    const int c0c = c0 / 64, clc = cl / 64;
+    const int NS = c0c * 8 + clc * 2, N1 = c0c * 8 + clc * 4;
+    const int ktot = 9 * c0 + 16 * cl;
+    const long long n_sh = 2ll * co_n * 2 * NS * 64, n_1 = (long long)co_n * 2 * N1 * 64;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_sh + n_1; i += (long long)gridDim.x * blockDim.x) {
+        const bool sh = i < n_sh;
+        const long long e = sh ? i : i - n_sh;
+        const int kw = 2 * (sh ? NS : N1) * 64;                     // row length
+        const int r = (int)(e / kw), k = (int)(e % kw);
+        const int j = k & 63, kb = k >> 6;
+        const int nb = sh ? NS : N1;
+        const int py = kb / nb, b = kb % nb;
+        const int co = sh ? r % co_n : r;
+        int px = sh ? r / co_n : 0;
+        float v = 0.f;
+        bool zero = false;
+        int src = 0;
+        if (b < c0c * 8) {                                           // skip block
+            const int iy = b & 1, plane = (b >> 1) & 3, ch = b >> 3;
+            const int qy = plane >> 1, qx = plane & 1;
+            const int nky = (qy != py) ? 2 : 1;
+            if (iy >= nky) zero = true;
+            const int ky = nky == 2 ? 2 * iy : 1;
+            const int kx = sh ? ((px == qx) ? 1 : (qx == 1 ? 2 : 0)) : (qx == 1 ? 0 : 2);
+            src = (ky * 3 + kx) * c0 + ch * 64 + j;
+        } else {
+            const int bl = b - c0c * 8;
+            int ch, dy, dx;
+            if (sh) { ch = bl >> 1; dy = bl & 1; dx = (px == 0) ? 1 : 0; }
+            else { ch = bl >> 2; dy = (bl >> 1) & 1; px = bl & 1; dx = px; }
+            src = 9 * c0 + (((py * 2 + px) * 4) + dy * 2 + dx) * cl + ch * 64 + j;
+        }
+        if (!zero) v = __bfloat162float(wm[(long long)co * ktot + src]);
+        (sh ? bsh : b1)[e] = __float2bfloat16_rn(v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ weight merge (checkpoint load time)
 // out[co][k]: k < 9*c0: skip weights [tap][c] = W3[co][c][tap];  then [cls = py*2+px][t = dy*2+dx][ci] =
 //   sum_{ky -> dy, kx -> dx} sum_cu W3[co][c0 + cu][ky][kx] * Wt[ci][cu][(py+ky-1)&1][(px+kx-1)&1]       (fp32 sums, one bf16 rounding)
@@ -440,9 +805,94 @@ static int launch_upm(const UpmMaps& maps, const CUtensorMap& mLow, const CUtens
     return ADN_OK;
 }
 
+static int launch_upm2(const UpmMaps& maps, const CUtensorMap& mLow, const CUtensorMap& mBsh, const CUtensorMap& mB1, Upm2Args& args,
+                       cudaStream_t stream) {
+    const int AUX = 2 * 128 * 4 + (2 * U_MAX_A + 2 * U_MAX_B + 4) * 8 + 16;
+    constexpr int MAX_DYN = 232448;
+    const int budget = MAX_DYN - 1024 - AUX - 2 * U_OUT_STAGE;
+    args.a_stages = 4;
+    int sl = (budget - args.a_stages * U2_A_STAGE) / U2_B_SLOT;
+    args.b_slots = sl > U_MAX_B ? U_MAX_B : sl;
+    if (args.b_slots < 4) return ADN_ERR_ARG;
+    const int smem = 1024 + args.a_stages * U2_A_STAGE + args.b_slots * U2_B_SLOT + 2 * U_OUT_STAGE + AUX;
+    const int max_pairs = num_sms() / 2;
+    const int grid = 2 * (args.work_total < max_pairs ? args.work_total : max_pairs);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(U_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static unsigned char smem_set[64] = {0};
+    ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_upm2_kernel<128>, MAX_DYN, smem_set));
+    ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_upm2_kernel<128>, maps, mLow, mBsh, mB1, args));
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
 }  // namespace adn
 
 using namespace adn;
+
+extern "C" int64_t adn_upmerged_pair_weight_elems(int c_out, int c0, int cl, int which) {
+    const int c0c = c0 / 64, clc = cl / 64;
+    return which == 0 ? 2ll * c_out * 2 * (c0c * 8 + clc * 2) * 64 : (long long)c_out * 2 * (c0c * 8 + clc * 4) * 64;
+}
+
+extern "C" int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_out, int c0, int cl, void* bsh, void* b1, void* stream) {
+    if (!w_merged || !bsh || !b1 || c_out <= 0 || c0 <= 0 || (c0 % 64) || cl <= 0 || (cl % 64)) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    upm2_repack_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w_merged, c_out, c0, cl, (__nv_bfloat16*)bsh,
+                                                                       (__nv_bfloat16*)b1);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
+                                                      const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
+                                                      const float* wb, void* out, void* stream) {
+    if (!skip || !low || !bsh || !b1 || !scale || !shift_m || !wb || !out) return ADN_ERR_ARG;
+    if (n <= 0 || h < 2 || w < 2 || hl < 1 || wl < 1 || c_out != 128) return ADN_ERR_ARG;
+    if (c0 <= 0 || (c0 % 64) || cl <= 0 || (cl % 64)) return ADN_ERR_ARG;
+    if (h - 2 * hl < 0 || h - 2 * hl > 1 || w - 2 * wl < 0 || w - 2 * wl > 1) return ADN_ERR_ARG;
+    if (!aligned16(skip) || !aligned16(low) || !aligned16(bsh) || !aligned16(b1) || !aligned16(out)) return ADN_ERR_ARG;
+    int st = check_device();
+    if (st != ADN_OK) return st;
+    Upm2Args args;
+    args.c0_chunks = c0 / 64; args.cl_chunks = cl / 64;
+    args.n_img = n; args.H = h; args.W = w; args.Hu = 2 * hl; args.Wu = 2 * wl;
+    const int hc = (h + 1) / 2, wc = (w + 1) / 2;
+    args.tiles_y = (hc + U_TH - 1) / U_TH;
+    const int tiles_x = (wc + U_TW - 1) / U_TW;
+    args.pair_img = (n % 2 == 0) ? 1 : 0;
+    args.ntx = args.pair_img ? tiles_x : (tiles_x + 1) / 2;
+    const int na = args.pair_img ? n / 2 : n;
+    const long long work = (long long)na * args.tiles_y * args.ntx * 2;
+    if (work > 0x7fffffffLL) return ADN_ERR_ARG;
+    args.work_total = (int)work;
+    args.div_ntx = make_fastdiv(args.ntx); args.div_ty = make_fastdiv(args.tiles_y);
+    args.scale = scale; args.shift = shift_m; args.wb = wb;
+    UpmMaps maps;
+    for (int p = 0; p < 4; ++p) {
+        st = make_plane_map(&maps.skip[p], skip, n, h, w, c0, p >> 1, p & 1, U_BW, U_BH);
+        if (st != ADN_OK) return st;
+        st = make_plane_map(&maps.out[p], out, n, h, w, c_out, p >> 1, p & 1, U_TW, U_TH);
+        if (st != ADN_OK) return st;
+    }
+    CUtensorMap mLow, mBsh, mB1;
+    st = make_act_map(&mLow, low, n, hl, wl, cl, U2_LOW_BW, U_BH);
+    if (st != ADN_OK) return st;
+    const int c0c = c0 / 64, clc = cl / 64;
+    st = make_weight_map(&mBsh, bsh, 2 * c_out, 2 * (c0c * 8 + clc * 2) * 64, 128);
+    if (st != ADN_OK) return st;
+    st = make_weight_map(&mB1, b1, c_out, 2 * (c0c * 8 + clc * 4) * 64, 64);
+    if (st != ADN_OK) return st;
+    return launch_upm2(maps, mLow, mBsh, mB1, args, (cudaStream_t)stream);
+}
 
 extern "C" int adn_conv3x3_upmerged_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
                                                  const void* w_merged, int c_out, const float* scale, const float* shift_m,

@@ -91,7 +91,7 @@ class UNet(nn.Module):
         self._packed_key = None
         self._engine = None
         self._ws = {}
-        # ConvTranspose2d + first decoder conv as one merged-weight kernel where the level has >= 256 output channels (ADN_UPMERGE=0: off)
+        # ConvTranspose2d + first decoder conv as one merged-weight kernel where the level has >= 128 output channels (ADN_UPMERGE=0: off)
         self.upmerge = os.environ.get("ADN_UPMERGE", "1") != "0"
         self.profile = None      # set to a list to record (layer, kind, flops, start_event, end_event) per kernel call
         self.launch_count = 0    # kernels launched by this module so far (bench.py's gpu_launches)
@@ -136,12 +136,12 @@ class UNet(nn.Module):
             packed[f"{name}.up"] = {"w": wp, "bias": sd[f"{name}.up.bias"].float().contiguous(), "co": co, "ci": ci, "keep": w}
             packed[f"{name}.0"] = conv(f"{name}.conv", 0, 1)
             packed[f"{name}.3"] = conv(f"{name}.conv", 3, 4)
-            # ConvTranspose2d merged into the first conv's weights (csrc/conv_upm.cu) for the levels with >= 256 output channels.
-            # Measured at batch 64 x (257,1034): upconv1 0.26 + 1.64 -> 1.63 ms, upconv2 0.32 + 1.58 -> 1.51 ms; the 128-wide
-            # level LOSES (0.38 + 1.65 -> 2.36 ms: a parity-class tile re-reads all four skip planes, 78 KB of TMA writes per
-            # 64-channel chunk against 23 KB, and a 256x128x16 UMMA is too short to hide them), so it keeps the two kernels.
+            # ConvTranspose2d merged into the first conv's weights (csrc/conv_upm.cu) for the levels with >= 128 output channels.
+            # Measured at batch 64 x (257,1034): upconv1 0.26 + 1.64 -> 1.63 ms, upconv2 0.32 + 1.58 -> 1.51 ms.  The 128-wide level
+            # LOSES with one parity class per tile (0.38 + 1.65 -> 2.36 ms: every class re-reads all four skip planes, and a
+            # 256x128x16 UMMA is too short to hide 78 KB of TMA writes per chunk), so it runs the two-classes-per-tile kernel.
             pc = packed[f"{name}.0"]
-            if pc["co"] % 256 == 0:
+            if pc["co"] % 128 == 0:
                 w3, bt = pc["keep"][0], packed[f"{name}.up"]["bias"]
                 c0 = pc["ci"] - co
                 wm = torch.empty((pc["co"], 9 * c0 + 16 * ci), dtype=torch.bfloat16, device=device)
@@ -150,7 +150,15 @@ class UNet(nn.Module):
                 _lib.check(lib.adn_pack_upmerged_weight_bf16(w3.data_ptr(), w.data_ptr(), bt.data_ptr(), pc["scale"].data_ptr(),
                                                              pc["shift"].data_ptr(), pc["co"], c0, co, ci, wm.data_ptr(),
                                                              shift_m.data_ptr(), wb.data_ptr(), s), "adn_pack_upmerged_weight_bf16")
-                packed[f"{name}.m"] = {"w": wm, "scale": pc["scale"], "shift": shift_m, "wb": wb, "co": pc["co"], "c0": c0, "cl": ci}
+                pm = {"w": wm, "scale": pc["scale"], "shift": shift_m, "wb": wb, "co": pc["co"], "c0": c0, "cl": ci}
+                if pc["co"] == 128:
+                    bsh = torch.empty(int(lib.adn_upmerged_pair_weight_elems(128, c0, ci, 0)), dtype=torch.bfloat16, device=device)
+                    b1 = torch.empty(int(lib.adn_upmerged_pair_weight_elems(128, c0, ci, 1)), dtype=torch.bfloat16, device=device)
+                    _lib.check(lib.adn_pack_upmerged_pair_weight_bf16(wm.data_ptr(), 128, c0, ci, bsh.data_ptr(), b1.data_ptr(), s),
+                               "adn_pack_upmerged_pair_weight_bf16")
+                    pm["bsh"], pm["b1"] = bsh, b1
+                if pc["co"] % 256 == 0 or pc["co"] == 128:
+                    packed[f"{name}.m"] = pm
         packed["out"] = {"w": sd["out.weight"].float().reshape(-1).contiguous(), "b": sd["out.bias"].float().contiguous()}
         return packed
 
@@ -237,10 +245,15 @@ class UNet(nn.Module):
             pm = pk.get(f"{name}.m") if self.upmerge else None
             if pm is not None:
                 # executed MACs: 9 taps over the skip channels + 4 merged taps over the low-resolution channels
-                timed(f"{name}.up+0", "conv3x3_upm", 2.0 * n * hs[l] * wz[l] * pm["co"] * (9 * pm["c0"] + 4 * pm["cl"]), 1,
-                      lib.adn_conv3x3_upmerged_bn_relu_bf16, ws[f"s{l}"].data_ptr(), pm["c0"], cur.data_ptr(), pm["cl"], hs[l + 1],
-                      wz[l + 1], n, hs[l], wz[l], pm["w"].data_ptr(), pm["co"], pm["scale"].data_ptr(), pm["shift"].data_ptr(),
-                      pm["wb"].data_ptr(), ws[f"ua{l}"].data_ptr(), s)
+                flops = 2.0 * n * hs[l] * wz[l] * pm["co"] * (9 * pm["c0"] + 4 * pm["cl"])
+                if "bsh" in pm:
+                    timed(f"{name}.up+0", "conv3x3_upm", flops, 1, lib.adn_conv3x3_upmerged_pair_bn_relu_bf16, ws[f"s{l}"].data_ptr(),
+                          pm["c0"], cur.data_ptr(), pm["cl"], hs[l + 1], wz[l + 1], n, hs[l], wz[l], pm["bsh"].data_ptr(), pm["b1"].data_ptr(),
+                          pm["co"], pm["scale"].data_ptr(), pm["shift"].data_ptr(), pm["wb"].data_ptr(), ws[f"ua{l}"].data_ptr(), s)
+                else:
+                    timed(f"{name}.up+0", "conv3x3_upm", flops, 1, lib.adn_conv3x3_upmerged_bn_relu_bf16, ws[f"s{l}"].data_ptr(), pm["c0"],
+                          cur.data_ptr(), pm["cl"], hs[l + 1], wz[l + 1], n, hs[l], wz[l], pm["w"].data_ptr(), pm["co"],
+                          pm["scale"].data_ptr(), pm["shift"].data_ptr(), pm["wb"].data_ptr(), ws[f"ua{l}"].data_ptr(), s)
                 conv(f"{name}.3", ws[f"ua{l}"], ch[l], None, 0, 0, 0, l, ws[f"ub{l}"])
                 cur = ws[f"ub{l}"]
                 continue

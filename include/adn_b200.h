@@ -185,6 +185,16 @@ int adn_conv3x3_upmerged_bn_relu_bf16(const void* skip, int c0, const void* low,
 int adn_pack_upmerged_weight_bf16(const float* w3, const float* wt, const float* bt, const float* scale, const float* shift,
                                   int c_out, int c0, int cup, int cl, void* w_merged, float* shift_m, float* wb, void* stream);
 
+/* The same merged layer for c_out == 128 (decoder level of 128 channels): both column-parity classes of a tile share one
+ * 256-column accumulator, so the skip planes are loaded once for two classes (csrc/conv_upm.cu, conv3x3_upm2_kernel).
+ * bsh / b1: adn_pack_upmerged_pair_weight_bf16 of the w_merged tensor above; adn_upmerged_pair_weight_elems(.., which) gives
+ * their element counts (which = 0: bsh, 1: b1).  shift_m / wb as above. */
+int64_t adn_upmerged_pair_weight_elems(int c_out, int c0, int cl, int which);
+int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_out, int c0, int cl, void* bsh, void* b1, void* stream);
+int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
+                                           const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
+                                           const float* wb, void* out_bf16, void* stream);
+
 /* MaxPool2d(2) on NHWC bf16 (model.py:26,31), floor semantics: (n,h,w,c) -> (n,h/2,w/2,c). */
 int adn_maxpool2x2_bf16(const void* src, int n, int h, int w, int c, void* out, void* stream);
 

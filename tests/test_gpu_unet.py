@@ -187,7 +187,8 @@ def test_conv3x3_64_output_channels_all_kernels(mode, n, c0, c1, h, w, relu):
 
 @pytest.mark.parametrize("exact_weights", [True, False])
 @pytest.mark.parametrize("n,c0,cl,co,hl,wl,h,w", [(2, 64, 128, 128, 8, 9, 17, 18), (1, 128, 256, 256, 5, 20, 10, 41), (3, 64, 128, 512, 17, 9, 35, 18),
-                                                  (2, 128, 128, 128, 1, 1, 2, 2), (4, 64, 64, 256, 33, 70, 66, 141)])
+                                                  (2, 128, 128, 128, 1, 1, 2, 2), (4, 64, 64, 256, 33, 70, 66, 141),
+                                                  (1, 64, 128, 128, 20, 37, 41, 75), (4, 128, 256, 128, 16, 33, 32, 67)])
 def test_conv3x3_upmerged_matches_convtranspose_pad_cat_conv(n, c0, cl, co, hl, wl, h, w, exact_weights):
     """UpSampleLayer.forward (model.py:41-50) up to the first ReLU -- ConvTranspose2d(k=2,s=2) + bias, F.pad to the skip's size,
     cat([skip, up]), Conv3x3 + folded BN + ReLU -- against the merged-weight kernel (csrc/conv_upm.cu), which never forms `up`.
@@ -223,14 +224,27 @@ def test_conv3x3_upmerged_matches_convtranspose_pad_cat_conv(n, c0, cl, co, hl, 
     _lib.check(lib.adn_conv3x3_upmerged_bn_relu_bf16(a0.data_ptr(), c0, a1.data_ptr(), cl, hl, wl, n, h, w, wm.data_ptr(), co,
                                                      sc.data_ptr(), shift_m.data_ptr(), wb.data_ptr(), out.data_ptr(), s))
     torch.cuda.synchronize()
-    got = from_nhwc(out.cpu())
-    assert torch.isfinite(got).all()
-    if exact_weights:
-        assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
-        assert nrel(got, ref) <= 2.5e-3
-    else:
-        assert float((got - ref).abs().max()) <= 1.2e-2 * float(ref.abs().max())
-        assert nrel(got, ref) <= 4e-3
+    outs = [out]
+    if co == 128:                 # the two-classes-per-tile kernel (conv3x3_upm2_kernel) on the same merged weights
+        import ctypes
+        lib.adn_upmerged_pair_weight_elems.restype = ctypes.c_int64
+        bsh = torch.empty(int(lib.adn_upmerged_pair_weight_elems(co, c0, cl, 0)), dtype=torch.bfloat16, device=d)
+        b1 = torch.empty(int(lib.adn_upmerged_pair_weight_elems(co, c0, cl, 1)), dtype=torch.bfloat16, device=d)
+        _lib.check(lib.adn_pack_upmerged_pair_weight_bf16(wm.data_ptr(), co, c0, cl, bsh.data_ptr(), b1.data_ptr(), s))
+        out2 = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=d)
+        _lib.check(lib.adn_conv3x3_upmerged_pair_bn_relu_bf16(a0.data_ptr(), c0, a1.data_ptr(), cl, hl, wl, n, h, w, bsh.data_ptr(), b1.data_ptr(),
+                                                              co, sc.data_ptr(), shift_m.data_ptr(), wb.data_ptr(), out2.data_ptr(), s))
+        torch.cuda.synchronize()
+        outs.append(out2)
+    for o in outs:
+        got = from_nhwc(o.cpu())
+        assert torch.isfinite(got).all()
+        if exact_weights:
+            assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+            assert nrel(got, ref) <= 2.5e-3
+        else:
+            assert float((got - ref).abs().max()) <= 1.2e-2 * float(ref.abs().max())
+            assert nrel(got, ref) <= 4e-3
 
 
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
