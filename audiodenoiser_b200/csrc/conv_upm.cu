@@ -563,7 +563,7 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
             if (!t.live) continue;
             const int Y = 2 * (t.ty * U_TH + ly) + t.py;
             uint32_t emask2[2] = {0u, 0u};
-            if (Y < a.H && t.img < a.n_img) {
+            if (a.cl_chunks > 0 && Y < a.H && t.img < a.n_img) {          // no low tensor (plain 3x3 conv in parity space): no bias terms
                 uint32_t ry = 0;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) if (Y + k - 1 < 0 || Y + k - 1 >= a.Hu) ry |= 1u << k;
@@ -844,7 +844,7 @@ extern "C" int64_t adn_upmerged_pair_weight_elems(int c_out, int c0, int cl, int
 }
 
 extern "C" int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_out, int c0, int cl, void* bsh, void* b1, void* stream) {
-    if (!w_merged || !bsh || !b1 || c_out <= 0 || c0 <= 0 || (c0 % 64) || cl <= 0 || (cl % 64)) return ADN_ERR_ARG;
+    if (!w_merged || !bsh || !b1 || c_out <= 0 || c0 <= 0 || (c0 % 64) || cl < 0 || (cl % 64)) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
     upm2_repack_kernel<<<num_sms() * 8, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w_merged, c_out, c0, cl, (__nv_bfloat16*)bsh,
                                                                        (__nv_bfloat16*)b1);
@@ -855,11 +855,14 @@ extern "C" int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_ou
 extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
                                                       const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
                                                       const float* wb, void* out, void* stream) {
-    if (!skip || !low || !bsh || !b1 || !scale || !shift_m || !wb || !out) return ADN_ERR_ARG;
-    if (n <= 0 || h < 2 || w < 2 || hl < 1 || wl < 1 || c_out != 128) return ADN_ERR_ARG;
-    if (c0 <= 0 || (c0 % 64) || cl <= 0 || (cl % 64)) return ADN_ERR_ARG;
-    if (h - 2 * hl < 0 || h - 2 * hl > 1 || w - 2 * wl < 0 || w - 2 * wl > 1) return ADN_ERR_ARG;
-    if (!aligned16(skip) || !aligned16(low) || !aligned16(bsh) || !aligned16(b1) || !aligned16(out)) return ADN_ERR_ARG;
+    if (!skip || !bsh || !b1 || !scale || !shift_m || !out) return ADN_ERR_ARG;
+    if (n <= 0 || h < 2 || w < 2 || c_out != 128) return ADN_ERR_ARG;
+    if (c0 <= 0 || (c0 % 64) || cl < 0 || (cl % 64)) return ADN_ERR_ARG;
+    if (cl > 0) {
+        if (!low || !wb || hl < 1 || wl < 1 || !aligned16(low)) return ADN_ERR_ARG;
+        if (h - 2 * hl < 0 || h - 2 * hl > 1 || w - 2 * wl < 0 || w - 2 * wl > 1) return ADN_ERR_ARG;
+    }
+    if (!aligned16(skip) || !aligned16(bsh) || !aligned16(b1) || !aligned16(out)) return ADN_ERR_ARG;
     int st = check_device();
     if (st != ADN_OK) return st;
     Upm2Args args;
@@ -884,7 +887,7 @@ extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, 
         if (st != ADN_OK) return st;
     }
     CUtensorMap mLow, mBsh, mB1;
-    st = make_act_map(&mLow, low, n, hl, wl, cl, U2_LOW_BW, U_BH);
+    if (cl > 0) st = make_act_map(&mLow, low, n, hl, wl, cl, U2_LOW_BW, U_BH); else mLow = maps.skip[0];
     if (st != ADN_OK) return st;
     const int c0c = c0 / 64, clc = cl / 64;
     st = make_weight_map(&mBsh, bsh, 2 * c_out, 2 * (c0c * 8 + clc * 2) * 64, 128);

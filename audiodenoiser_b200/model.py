@@ -93,6 +93,8 @@ class UNet(nn.Module):
         self._ws = {}
         # ConvTranspose2d + first decoder conv as one merged-weight kernel where the level has >= 128 output channels (ADN_UPMERGE=0: off)
         self.upmerge = os.environ.get("ADN_UPMERGE", "1") != "0"
+        # the 128-output-channel convs without a fused pool in the two-classes-per-tile parity formulation (ADN_PLANE128=0: off)
+        self.plane128 = os.environ.get("ADN_PLANE128", "1") != "0"
         self.profile = None      # set to a list to record (layer, kind, flops, start_event, end_event) per kernel call
         self.launch_count = 0    # kernels launched by this module so far (bench.py's gpu_launches)
 
@@ -121,7 +123,13 @@ class UNet(nn.Module):
                 return {"w": w, "scale": scale, "shift": shift, "co": co, "ci": ci, "keep": args}
             wp = torch.empty((co, 9, ci), dtype=torch.bfloat16, device=device)
             _lib.check(lib.adn_pack_conv3x3_weight_bf16(w.data_ptr(), co, ci, wp.data_ptr(), s), "adn_pack_conv3x3_weight_bf16")
-            return {"w": wp, "scale": scale, "shift": shift, "co": co, "ci": ci, "keep": (w, args)}
+            d = {"w": wp, "scale": scale, "shift": shift, "co": co, "ci": ci, "keep": (w, args)}
+            if co == 128 and ci >= 128:         # parity-class formulation with two classes per tile (conv3x3_upm2_kernel without a low tensor)
+                d["bsh"] = torch.empty(int(lib.adn_upmerged_pair_weight_elems(128, ci, 0, 0)), dtype=torch.bfloat16, device=device)
+                d["b1"] = torch.empty(int(lib.adn_upmerged_pair_weight_elems(128, ci, 0, 1)), dtype=torch.bfloat16, device=device)
+                _lib.check(lib.adn_pack_upmerged_pair_weight_bf16(wp.data_ptr(), 128, ci, 0, d["bsh"].data_ptr(), d["b1"].data_ptr(), s),
+                           "adn_pack_upmerged_pair_weight_bf16")
+            return d
 
         for name in ("downconv1", "downconv2", "downconv3", "downconv4"):
             packed[f"{name}.0"] = conv(f"{name}.conv", 0, 1, first=(name == "downconv1"))
@@ -221,6 +229,12 @@ class UNet(nn.Module):
         def conv(layer, src0, c0, src1, c1, h1, w1, lvl, dst, pool=None):
             p = pk[layer]
             flops = 2.0 * n * hs[lvl] * wz[lvl] * p["co"] * 9 * (c0 + c1)
+            # measured at batch 64 x (257,1034): upconv3.3 (128 -> 128) 0.89 -> 0.80 ms; downconv2.0 (64 -> 128, one chunk) 0.61 -> 0.62: not used
+            if self.plane128 and "bsh" in p and src1 is None and pool is None and c0 >= 128 and hs[lvl] >= 2 and wz[lvl] >= 2:
+                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_upmerged_pair_bn_relu_bf16, src0.data_ptr(), c0, 0, 0, 0, 0, n, hs[lvl],
+                      wz[lvl], p["bsh"].data_ptr(), p["b1"].data_ptr(), 128, p["scale"].data_ptr(), p["shift"].data_ptr(), 0,
+                      dst.data_ptr(), s)
+                return
             # the 2x2 max-pool of DownSampleLayer (model.py:31) is fused into the conv epilogue when `pool` is given
             timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,
                   src1.data_ptr() if src1 is not None else 0, c1, h1, w1, n, hs[lvl], wz[lvl], p["w"].data_ptr(), p["co"],

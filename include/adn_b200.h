@@ -188,7 +188,9 @@ int adn_pack_upmerged_weight_bf16(const float* w3, const float* wt, const float*
 /* The same merged layer for c_out == 128 (decoder level of 128 channels): both column-parity classes of a tile share one
  * 256-column accumulator, so the skip planes are loaded once for two classes (csrc/conv_upm.cu, conv3x3_upm2_kernel).
  * bsh / b1: adn_pack_upmerged_pair_weight_bf16 of the w_merged tensor above; adn_upmerged_pair_weight_elems(.., which) gives
- * their element counts (which = 0: bsh, 1: b1).  shift_m / wb as above. */
+ * their element counts (which = 0: bsh, 1: b1).  shift_m / wb as above.
+ * cl == 0 (low = wb = NULL, w_merged = the [c_out][9][c0] pack of adn_pack_conv3x3_weight_bf16): a plain Conv3x3 + BN + ReLU over
+ * `skip` in the same parity-class formulation, used for the 128-output-channel layers without a fused pool. */
 int64_t adn_upmerged_pair_weight_elems(int c_out, int c0, int cl, int which);
 int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_out, int c0, int cl, void* bsh, void* b1, void* stream);
 int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,

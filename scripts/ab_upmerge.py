@@ -13,13 +13,13 @@ batch = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 net = UNet().eval()
 net.load_state_dict(seeded_state_dict(3))
 x = torch.rand(batch, 1, 257, 1034, device="cuda")
-MODES = {"two-kernel": False, "merged": True}
+MODES = {"two-kernel": (False, False), "merged": (True, False), "merged+plane128": (True, True)}
 res = {m: {} for m in MODES}
 outs = {}
 with torch.no_grad():
     for rep in range(6):
         for mode, flag in MODES.items():
-            net.upmerge = flag
+            net.upmerge, net.plane128 = flag
             net.profile = []
             y = net(x)
             torch.cuda.synchronize()
@@ -32,7 +32,7 @@ with torch.no_grad():
 tot = {}
 for m in MODES:
     tot[m] = sum(v[0] / v[1] for v in res[m].values())
-    print(m, "  ".join(f"{k} {v[0] / v[1]:.3f} ({v[2] / (v[0] / v[1]) / 1e9:.0f} TF)" for k, v in res[m].items() if k.startswith("upconv")))
+    print(m, "  ".join(f"{k} {v[0] / v[1]:.3f} ({v[2] / (v[0] / v[1]) / 1e9:.0f} TF)" for k, v in res[m].items() if k.startswith("upconv") or k.startswith("downconv2")))
 print("forward total: " + ", ".join(f"{m} {tot[m]:.3f} ms" for m in MODES))
-a, b = outs["two-kernel"], outs["merged"]
-print(f"merged vs two-kernel output: norm-rel {((a - b).norm() / a.norm()).item():.3e}")
+a, b, c = outs["two-kernel"], outs["merged"], outs["merged+plane128"]
+print(f"merged vs two-kernel output: norm-rel {((a - b).norm() / a.norm()).item():.3e}; plane128 vs merged: max abs {(b - c).abs().max().item():.3e}")

@@ -247,6 +247,38 @@ def test_conv3x3_upmerged_matches_convtranspose_pad_cat_conv(n, c0, cl, co, hl, 
             assert nrel(got, ref) <= 4e-3
 
 
+@pytest.mark.parametrize("n,c0,h,w", [(2, 128, 17, 18), (1, 64, 40, 75), (4, 128, 32, 67), (3, 256, 2, 2), (2, 128, 128, 517)])
+def test_conv3x3_parity_class_kernel_without_low_tensor(n, c0, h, w):
+    """conv3x3_upm2_kernel with cl = 0 is a plain Conv3x3 + BN + ReLU with 128 output channels computed per row-parity class (two
+    column-parity classes per tile): against F.conv2d on the same bf16 operands, odd and even sizes, one and several tiles."""
+    import ctypes
+    lib = _lib.load(); s = _lib.stream_ptr()
+    lib.adn_upmerged_pair_weight_elems.restype = ctypes.c_int64
+    co = 128
+    g = torch.Generator().manual_seed(h * 7 + w)
+    x = bf16_round(torch.randn(n, c0, h, w, generator=g))
+    wt = bf16_round(torch.randn(co, c0, 3, 3, generator=g) * (2.0 / (9 * c0)) ** 0.5)
+    scale = 0.5 + torch.rand(co, generator=g); shift = 0.1 * torch.randn(co, generator=g)
+    ref = F.relu(F.conv2d(x, wt, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    d = dev()
+    wp = torch.empty((co, 9, c0), dtype=torch.bfloat16, device=d)
+    wd = wt.to(d).contiguous()
+    _lib.check(lib.adn_pack_conv3x3_weight_bf16(wd.data_ptr(), co, c0, wp.data_ptr(), s))
+    bsh = torch.empty(int(lib.adn_upmerged_pair_weight_elems(co, c0, 0, 0)), dtype=torch.bfloat16, device=d)
+    b1 = torch.empty(int(lib.adn_upmerged_pair_weight_elems(co, c0, 0, 1)), dtype=torch.bfloat16, device=d)
+    _lib.check(lib.adn_pack_upmerged_pair_weight_bf16(wp.data_ptr(), co, c0, 0, bsh.data_ptr(), b1.data_ptr(), s))
+    a0 = to_nhwc_bf16(x).to(d)
+    out = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=d)
+    sc, sh = scale.to(d), shift.to(d)
+    _lib.check(lib.adn_conv3x3_upmerged_pair_bn_relu_bf16(a0.data_ptr(), c0, 0, 0, 0, 0, n, h, w, bsh.data_ptr(), b1.data_ptr(), co,
+                                                          sc.data_ptr(), sh.data_ptr(), 0, out.data_ptr(), s))
+    torch.cuda.synchronize()
+    got = from_nhwc(out.cpu())
+    assert torch.isfinite(got).all()
+    assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+    assert nrel(got, ref) <= 2.5e-3
+
+
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
 def test_convt2x2(n, ci, co, h, w):
     lib = _lib.load(); s = _lib.stream_ptr()
