@@ -420,9 +420,10 @@ def run_b200(args):
                     tc[k] += agg[kind][k]
         tc_tflops = tc["flops"] / (tc["ms"] * 1e-3) / 1e12 if tc["ms"] > 0 else 0.0
         peak_tc = peaks["bf16_sustained"]
-        roofline = {"kernel": "conv3x3_halo_kernel + conv3x3_dx_kernel + conv3x3_upm_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU: 12 + 3 + 2 launches/step; the 64-output-channel layers incl. the head-fused one run the kx-in-N variant, the first conv of decoder levels 1-2 runs with the ConvTranspose2d merged into its weights and is counted with the FLOPs it executes)", "bound": "tensor",
+        roofline = {"kernel": "conv3x3_halo_kernel + conv3x3_dx_kernel + conv3x3_upm_kernel / conv3x3_upm2_kernel (tcgen05 implicit-GEMM Conv3x3+BN+ReLU: 10 + 3 + 4 launches/step; the 64-output-channel layers incl. the head-fused one run the kx-in-N variant; the first conv of decoder levels 1-3 runs with the ConvTranspose2d merged into its weights and is counted with the FLOPs it EXECUTES (9 skip + 4 merged taps), not with those of the two layers it replaces)", "bound": "tensor",
                     "achieved": tc_tflops, "peak": peak_tc, "unit": "TFLOP/s", "frac": tc_tflops / peak_tc,
-                    "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+                    "peak_source": f"MEASURED_PEAKS bf16_tflops_sustained ({peaks['source']}: cuBLAS 8192^3 back to back, power-capped); kernel timed inside a long step.  frac > 1 means these kernels hold higher clocks under the same power cap than the cuBLAS GEMM the peak was measured with",
+                    "frac_of_burst_peak": tc_tflops / peaks["bf16_burst"], "burst_peak": peaks["bf16_burst"],
                     "launches_per_step": tc["launches"] // reps, "avg_launch_ms": tc["ms"] / max(tc["launches"], 1),
                     "algorithmic_flops_per_step": tc["flops"] / reps, "traffic": None}
         try:                                   # measured DRAM bytes per launch of the same kernel, from the committed ncu capture
