@@ -199,7 +199,6 @@ class UNet(nn.Module):
             ws[f"s{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)      # second conv = skip / bottleneck out
             if l < 4:
                 ws[f"p{l}"] = torch.empty((n, hs[l + 1], wsz[l + 1], ch[l]), **bf)          # pooled
-                ws[f"u{l}"] = torch.empty((n, 2 * hs[l + 1], 2 * wsz[l + 1], ch[l]), **bf)  # up-sampled into level l
                 ws[f"ua{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
                 if l > 0:                      # level 0's second decoder conv feeds the fused 1x1 head instead
                     ws[f"ub{l}"] = torch.empty((n, hs[l], wsz[l], ch[l]), **bf)
@@ -271,6 +270,8 @@ class UNet(nn.Module):
                 conv(f"{name}.3", ws[f"ua{l}"], ch[l], None, 0, 0, 0, l, ws[f"ub{l}"])
                 cur = ws[f"ub{l}"]
                 continue
+            if f"u{l}" not in ws:            # the up-sampled map exists only where the ConvTranspose is not merged into the conv (level 0)
+                ws[f"u{l}"] = torch.empty((n, 2 * hs[l + 1], 2 * wz[l + 1], ch[l]), dtype=torch.bfloat16, device=x.device)
             timed(f"{name}.up", "convt2x2", 2.0 * n * hs[l + 1] * wz[l + 1] * pu["ci"] * 4 * pu["co"], 1, lib.adn_convt2x2_bf16,
                   cur.data_ptr(), pu["ci"], n, hs[l + 1], wz[l + 1], pu["w"].data_ptr(), pu["co"], pu["bias"].data_ptr(),
                   ws[f"u{l}"].data_ptr(), s)
