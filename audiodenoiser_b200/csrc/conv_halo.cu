@@ -46,6 +46,7 @@ struct HaloArgs {
     int a_stages, b_slots, b_resident;
     float relu_floor;              // 0 = ReLU, -inf = no activation (train-mode pre-BN output, dgrad)
     int tma_store;                 // epilogue stages bf16 tiles in smem and stores them with TMA (when the smem budget allows)
+    int warp_store;                // each epilogue warp stores its own 32-pixel x 64-channel box (no CTA-wide barrier in the epilogue)
     const float* scale;
     const float* shift;
     __nv_bfloat16* out;
@@ -328,8 +329,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     o_stage = smem_base + stage_off + buf * H_OUT_STAGE;
                     p_stage = smem_base + stage_off + 2u * H_OUT_STAGE + buf * H_POOL_STAGE;
                     if (first_half) {                                 // this buffer's previous TMA store must have read it
-                        if (et == 0) bulk_wait_read<1>();
-                        named_bar_sync(1, H_EPI_THREADS);
+                        if (a.warp_store) { if (lane == 0) bulk_wait_read<1>(); __syncwarp(); }
+                        else { if (et == 0) bulk_wait_read<1>(); named_bar_sync(1, H_EPI_THREADS); }
                     }
                     const uint32_t rbase = o_stage + (uint32_t)row * 128u;
 #pragma unroll
@@ -368,12 +369,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                 }
                 if (a.tma_store && !first_half) {                     // a 64-channel group is staged: hand it to the TMA engine
                     fence_proxy_async();
-                    named_bar_sync(1, H_EPI_THREADS);
-                    if (et == 0) {
-                        const int ch0 = n_blk * BLOCK_N + (c0 - 32);
-                        tma_store_4d(&tmOut, o_stage, ch0, tx * H_TW, ty * H_TH, img);
-                        if (a.pool_out) tma_store_4d(&tmPool, p_stage, ch0, tx * (H_TW / 2), ty * (H_TH / 2), img);
-                        bulk_commit();
+                    const int ch0 = n_blk * BLOCK_N + (c0 - 32);
+                    if (a.warp_store) {                               // this warp's 4 tile rows (32 pixels) / 2 pooled rows: its own boxes
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_4d(&tmOut, o_stage + (uint32_t)quad * 4096u, ch0, tx * H_TW, ty * H_TH + quad * 4, img);
+                            if (a.pool_out) tma_store_4d(&tmPool, p_stage + (uint32_t)quad * 1024u, ch0, tx * (H_TW / 2), ty * (H_TH / 2) + quad * 2, img);
+                            bulk_commit();
+                        }
+                    } else {
+                        named_bar_sync(1, H_EPI_THREADS);
+                        if (et == 0) {
+                            tma_store_4d(&tmOut, o_stage, ch0, tx * H_TW, ty * H_TH, img);
+                            if (a.pool_out) tma_store_4d(&tmPool, p_stage, ch0, tx * (H_TW / 2), ty * (H_TH / 2), img);
+                            bulk_commit();
+                        }
                     }
                     ++store_groups;
                 }
@@ -399,7 +409,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (a.tma_store && et == 0) bulk_wait<0>();                    // smem must outlive the last bulk stores
+        if (a.tma_store && (a.warp_store ? lane == 0 : et == 0)) bulk_wait<0>();     // smem must outlive the last bulk stores
     }
 
     tc_fence_before();
@@ -415,7 +425,9 @@ static int g_halo_pitch = 10;    // 10: dense halo tile; 16: padded rows
 static int g_halo_stages = 0;    // > 0: A stages of the streaming-B configuration (tuning hook)
 // tuning hook bits: 1 = CTA pairs also for the one-chunk 128-wide layer (measured: downconv2.0 0.63 -> 0.87 ms, off);
 // 2 = stream the weights when keeping them resident would cost the TMA-store epilogue its staging buffers (measured at batch 64:
-// downconv2.3 1.15 -> 1.02 ms, downconv2.0 0.63 -> 0.60, upconv3.3 0.92 -> 0.90; on)
+// downconv2.3 1.15 -> 1.02 ms, downconv2.0 0.63 -> 0.60, upconv3.3 0.92 -> 0.90; on);
+// 4 = every epilogue warp stores its own 32-pixel box, no CTA-wide barrier in the epilogue (measured: downconv2.3 1.00 -> 0.96 ms,
+// every other layer within noise, forward total unchanged: the epilogue barriers are not what holds the 128-wide layers back; off)
 static int g_halo_tune = 2;
 
 template <int BLOCK_N, int NCTA, int H_PITCH>
@@ -537,10 +549,12 @@ static int conv3x3_halo(const void* src0, int c0, const void* src1, int c1, int 
 
     // output maps for the TMA-store epilogue: box {64 ch, 8 px, 16 rows} of the NHWC output, {64, 4, 8} of the pooled one
     CUtensorMap mOut = mA0, mPool = mA0;
+    args.warp_store = (g_halo_tune & 4) ? 1 : 0;
     if (epi == HEPI_NHWC) {
-        st = make_act_map(&mOut, out, n, h, w, c_out, H_TW, H_TH);
+        const int div = args.warp_store ? 4 : 1;                    // per-warp boxes: a quarter of the tile's rows
+        st = make_act_map(&mOut, out, n, h, w, c_out, H_TW, H_TH / div);
         if (st != ADN_OK) return st;
-        if (pool_out) st = make_act_map(&mPool, pool_out, n, h / 2, w / 2, c_out, H_TW / 2, H_TH / 2);
+        if (pool_out) st = make_act_map(&mPool, pool_out, n, h / 2, w / 2, c_out, H_TW / 2, H_TH / 2 / div);
         if (st != ADN_OK) return st;
     }
 

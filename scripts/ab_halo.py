@@ -18,7 +18,7 @@ for f in (lib.adn__conv_halo_pitch, lib.adn__conv_pair_mode, lib.adn__conv_halo_
 net = UNet().eval()
 net.load_state_dict(seeded_state_dict(3))
 x = torch.rand(batch, 1, 257, 1034, device="cuda")
-MODES = {"pitch16,pair128,resident": (16, 1, 0, 0), "pitch10": (10, 1, 0, 0), "+pair256": (10, 3, 0, 0), "+stream-for-tma-store (default)": (10, 3, 0, 2)}
+MODES = {"default": (10, 3, 0, 2), "per-warp-stores": (10, 3, 0, 6)}
 res = {m: {} for m in MODES}
 outs = {}
 with torch.no_grad():

@@ -125,7 +125,7 @@ def test_conv3x3_pair_and_pitch_variants_bit_equal(co):
     sc = (0.5 + torch.rand(co, generator=g)).to(dev()); sh = (0.1 * torch.randn(co, generator=g)).to(dev())
     outs = []
     try:
-        for pair, pitch, tune in ((0, 10, 2), (1, 10, 2), (3, 10, 2), (3, 16, 0), (0, 16, 0), (3, 10, 0), (1, 10, 1)):
+        for pair, pitch, tune in ((0, 10, 2), (1, 10, 2), (3, 10, 2), (3, 16, 0), (0, 16, 0), (3, 10, 0), (1, 10, 1), (3, 10, 6), (0, 10, 6)):
             lib.adn__conv_pair_mode(pair); lib.adn__conv_halo_pitch(pitch); lib.adn__conv_halo_tune(tune)
             out = torch.zeros((n, h, w, co), dtype=torch.bfloat16, device=dev())
             pool = torch.zeros((n, h // 2, w // 2, co), dtype=torch.bfloat16, device=dev())
