@@ -63,7 +63,7 @@ struct PackEntry {
     int c_out, c_in, kind, pad;          // kind 0: Conv2d 3x3 (Co,Ci,3,3); 1: ConvTranspose2d 2x2 (Ci,Co,2,2)
 };
 __global__ void __launch_bounds__(256)
-pack_table_kernel(const PackEntry* __restrict__ table) {
+pack_table_kernel(const PackEntry* __restrict__ table, int which) {      // which: bit 0 = forward packs, bit 1 = data-gradient packs
     __shared__ float tile[32][32 * 9 + 1];                        // [co][ci * 9 + tap], odd pitch: conflict-free both ways
     const PackEntry e = table[blockIdx.y];
     const int co_n = e.c_out, ci_n = e.c_in;
@@ -79,11 +79,11 @@ pack_table_kernel(const PackEntry* __restrict__ table) {
                 for (int i = threadIdx.x; i < 288; i += 256) tile[r][i] = src[i];
             }
             __syncthreads();
-            for (int it = grp; it < 288; it += 8) {               // it = co_l * 9 + tap: 32 consecutive ci
+            for (int it = grp; it < 288 && (which & 1); it += 8) {               // it = co_l * 9 + tap: 32 consecutive ci
                 const int co_l = it / 9, tap = it - co_l * 9;
                 e.fwd[((long long)(co0 + co_l) * 9 + tap) * ci_n + ci0 + l] = __float2bfloat16_rn(tile[co_l][l * 9 + tap]);
             }
-            for (int it = grp; it < 288; it += 8) {               // it = ci_l * 9 + tapd: 32 consecutive co, flipped tap
+            for (int it = grp; it < 288 && (which & 2); it += 8) {               // it = ci_l * 9 + tapd: 32 consecutive co, flipped tap
                 const int ci_l = it / 9, tapd = it - ci_l * 9;
                 e.dgrad[((long long)(ci0 + ci_l) * 9 + tapd) * co_n + co0 + l] = __float2bfloat16_rn(tile[l][ci_l * 9 + (8 - tapd)]);
             }
@@ -93,13 +93,13 @@ pack_table_kernel(const PackEntry* __restrict__ table) {
         const long long stride = (long long)gridDim.x * blockDim.x;
         const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
         const long long total = 4ll * co_n * ci_n;
-        for (long long i = i0; i < total; i += stride) {          // fwd [q][co][ci]
+        for (long long i = i0; i < total && (which & 1); i += stride) {          // fwd [q][co][ci]
             const int ci = (int)(i % ci_n);
             const int co = (int)((i / ci_n) % co_n);
             const int q = (int)(i / ((long long)ci_n * co_n));
             e.fwd[i] = __float2bfloat16_rn(e.w[((long long)ci * co_n + co) * 4 + q]);
         }
-        for (long long i = i0; i < total; i += stride) {          // dgrad [ci][q * Co + co]
+        for (long long i = i0; i < total && (which & 2); i += stride) {          // dgrad [ci][q * Co + co]
             const int co = (int)(i % co_n);
             const int q = (int)((i / co_n) % 4);
             const int ci = (int)(i / (4ll * co_n));
@@ -349,12 +349,16 @@ extern "C" int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int
     return ADN_OK;
 }
 
-extern "C" int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stream) {
-    if (!table_dev || n_entries <= 0 || n_entries > 65535) return ADN_ERR_ARG;
+extern "C" int adn_pack_weights_table_sel_bf16(const void* table_dev, int n_entries, int which, void* stream) {
+    if (!table_dev || n_entries <= 0 || n_entries > 65535 || which < 1 || which > 3) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    pack_table_kernel<<<dim3(1024, (unsigned)n_entries), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev));
+    pack_table_kernel<<<dim3(1024, (unsigned)n_entries), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev), which);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
+}
+
+extern "C" int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stream) {
+    return adn_pack_weights_table_sel_bf16(table_dev, n_entries, 3, stream);
 }
 
 extern "C" int adn_fold_bn_f32(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,

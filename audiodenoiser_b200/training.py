@@ -97,6 +97,11 @@ class TrainEngine:
         self.loss_out = torch.empty(4, dtype=torch.float32, device=dev)
         self._loss_ws = None
         self._wg_stream = None
+        self._aux_stream = None
+        self._dgrad_stale = False
+        # ADN_SPLIT_PACK=1: data-gradient weight packs on a side stream under the forward instead of behind AdamW.  Measured SLOWER
+        # (3.62 -> 3.74 ms at batch 16: the fp32 weights are read twice and the pack competes with the latency-bound forward kernels): off
+        self.split_pack = os.environ.get("ADN_SPLIT_PACK", "0") == "1"
         self.overlap_wgrad = os.environ.get("ADN_OVERLAP_WGRAD", "1") != "0"      # weight gradients on a side stream (backward())
 
         # ---- layer table: (key prefix, conv idx, bn idx, level, c0, c1, co)
@@ -187,16 +192,23 @@ class TrainEngine:
         self._pack_n = len(rows)
         self._pack_table = torch.from_numpy(host.view(np.uint8).copy()).to(self.device)
 
-    def repack(self):
+    def repack(self, which: int = 3):
         """fp32 master weights -> bf16 GEMM operands (forward [Co][tap][Ci], data gradient [Ci][8-tap][Co]; convT likewise): one
-        launch over a device-side table of all 21 conv / convT weights, once per optimizer step."""
+        launch over a device-side table of all 21 conv / convT weights.  which: 1 = forward operands, 2 = data-gradient operands,
+        3 = both.  train_step packs the forward operands after AdamW and the data-gradient operands on a side stream under the next
+        forward (they are first read in backward)."""
         if self._pack_table is None:
             self._build_pack_table()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.adn_pack_weights_table_bf16(self._pack_table.data_ptr(), self._pack_n, _lib.stream_ptr()), "pack weights")
+            _lib.check(self.lib.adn_pack_weights_table_sel_bf16(self._pack_table.data_ptr(), self._pack_n, which, _lib.stream_ptr()), "pack weights")
         self.launch_count += 1
-        self.model._packed = None          # the eval-mode forward of the module repacks from the updated parameters
-        self._packed_versions = self._versions()
+        if which & 1:
+            self.model._packed = None          # the eval-mode forward of the module repacks from the updated parameters
+            self._packed_versions = self._versions()
+        if which & 2:
+            self._dgrad_stale = False
+        else:
+            self._dgrad_stale = True
 
     # ------------------------------------------------------------------ forward (model.py:70-94 in train() mode)
     def forward(self, x):
@@ -282,6 +294,8 @@ class TrainEngine:
         bf = dict(dtype=torch.bfloat16, device=self.device)
         d_out = d_out.float().contiguous()
         wsp = self.ws.data_ptr()
+        if self._dgrad_stale:                  # a backward outside train_step after a step that packed the forward operands only
+            self.repack(2)
         main = torch.cuda.current_stream(self.device)
         if self._wg_stream is None:
             self._wg_stream = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
@@ -442,7 +456,7 @@ class TrainEngine:
         from .sharding import average_gradients_
         average_gradients_(self.G, self.group)
 
-    def optimizer_step(self):
+    def optimizer_step(self, split_pack: bool = False):
         """clip_grad_norm_(max_norm) + AdamW.step(), then refresh the bf16 operand copies.  Returns the gradient norm (device scalar)."""
         lib, s = self.lib, _lib.stream_ptr()
         self.step_count += 1
@@ -452,21 +466,32 @@ class TrainEngine:
                                                   self.norm_coef.data_ptr(), self.step_dev.data_ptr(), self.lr, self.betas[0], self.betas[1],
                                                   self.eps, self.weight_decay, s), "adamw")
         self.launch_count += 4
-        self.repack()
+        self.repack(1 if split_pack else 3)
         return self.norm_coef[0]
 
     def train_step(self, noisy, clean):
         """One iteration of train_one_epoch (train.py:65-72).  Returns the device tensor (total, stft, mel, l1)."""
-        self.zero_grad()
+        # zeroing the gradient buffer and the data-gradient weight packs (stale since the last step's AdamW) are first needed in
+        # backward: they run on a side stream under the forward
+        main = torch.cuda.current_stream(self.device)
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(self.device)
+        aux = self._aux_stream if self.split_pack else main
+        aux.wait_stream(main)
+        with torch.cuda.stream(aux):
+            self.zero_grad()
+            if self._dgrad_stale:
+                self.repack(2)
         out = self.forward(noisy)
         losses, d_pred = self.loss_and_grad(out, clean)
+        main.wait_stream(aux)
         self._bucketed = True
         try:
             self.backward(d_pred)
         finally:
             self._bucketed = False
         self.all_reduce_grads()
-        self.optimizer_step()
+        self.optimizer_step(split_pack=self.split_pack)
         return losses
 
     def release_graph(self):

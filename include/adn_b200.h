@@ -256,6 +256,9 @@ int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int c_out, voi
  *   struct { const float* w; void* fwd_bf16; void* dgrad_bf16; int32_t c_out, c_in, kind, pad; }   (32 bytes)
  * kind 0 = Conv2d 3x3 (fwd [Co][tap][Ci], dgrad [Ci][8-tap][Co]); kind 1 = ConvTranspose2d 2x2 (fwd [q][Co][Ci], dgrad [Ci][q*Co+co]). */
 int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stream);
+/* The same with a selection: which = 1 forward packs only, 2 data-gradient packs only, 3 both (the training step packs the forward
+ * operands after AdamW and the data-gradient operands on a side stream under the next forward). */
+int adn_pack_weights_table_sel_bf16(const void* table_dev, int n_entries, int which, void* stream);
 
 /* nn.BatchNorm2d in train() mode (model.py:12,15; eps 1e-5, momentum 0.1): batch statistics of z (pixels, c) NHWC bf16 ->
  * scale = gamma * invstd, shift = beta - mean * scale, mean, invstd; running_mean / running_var are updated in place
