@@ -50,6 +50,7 @@ SIGNATURES = {
     "adn_upmerged_pair_weight_elems": (c_int64, [c_int, c_int, c_int, c_int]),
     "adn_pack_upmerged_pair_weight_bf16": (c_int, [P, c_int, c_int, c_int, P, P, P]),
     "adn_conv3x3_upmerged_pair_bn_relu_bf16": (c_int, [P, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P]),
+    "adn_conv3x3_pair_bn_relu_pool_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, P, P, P, P, P]),
     "adn_maxpool2x2_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "adn_nhwc_bf16_to_nchw_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "adn_nchw_f32_to_nhwc_bf16": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),

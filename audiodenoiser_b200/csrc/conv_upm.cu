@@ -349,16 +349,18 @@ struct Upm2Args {
     int n_img, H, W, Hu, Wu;
     int tiles_y, ntx, pair_img, work_total;
     FastDiv div_ntx, div_ty;
-    int a_stages, b_slots;
+    int a_stages, b_slots, a_stage_bytes;
+    int pool;                      // fused MaxPool2d(2) of the output (plain conv only): (n, H/2, W/2, CO) through tmPool
     const float* scale;
     const float* shift;
     const float* wb;
 };
 
-template <int CO>
+template <int CO, bool POOL>
 __global__ void __launch_bounds__(U_THREADS, 1)
 conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant__ CUtensorMap tmLow,
-                    const __grid_constant__ CUtensorMap tmBsh, const __grid_constant__ CUtensorMap tmB1, const Upm2Args a) {
+                    const __grid_constant__ CUtensorMap tmBsh, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmPool, const Upm2Args a) {
     constexpr int BLOCK_N = 2 * CO;
     static_assert(BLOCK_N == 256, "two classes of 128 output channels");
     constexpr int TMEM_COLS = 2 * BLOCK_N;
@@ -369,9 +371,11 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
     uint8_t* smem_gen = smem_dyn + (smem_base - smem_u32(smem_dyn));
 
     const uint32_t a_base = smem_base;
-    const uint32_t b_base = a_base + (uint32_t)a.a_stages * U2_A_STAGE;
-    const uint32_t stage_off = (uint32_t)a.a_stages * U2_A_STAGE + (uint32_t)a.b_slots * U2_B_SLOT;
-    const uint32_t aux_off = stage_off + 2u * U_OUT_STAGE;
+    const uint32_t A_STAGE = (uint32_t)a.a_stage_bytes;
+    const uint32_t b_base = a_base + (uint32_t)a.a_stages * A_STAGE;
+    const uint32_t stage_off = (uint32_t)a.a_stages * A_STAGE + (uint32_t)a.b_slots * U2_B_SLOT;
+    const uint32_t pool_off = stage_off + 2u * U_OUT_STAGE;              // POOL: two more [128 px][64 ch] staging tiles
+    const uint32_t aux_off = pool_off + (POOL ? 2u * U_OUT_STAGE : 0u);
     float* s_scale = reinterpret_cast<float*>(smem_gen + aux_off);
     float* s_shift = s_scale + CO;
     const uint32_t aux_f32 = (uint32_t)(2 * CO) * 4;
@@ -389,6 +393,7 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
     if (warp == 0 && lane == 0) {
         for (int p = 0; p < 4; ++p) { tma_prefetch_desc(&maps.skip[p]); tma_prefetch_desc(&maps.out[p]); }
         tma_prefetch_desc(&tmLow); tma_prefetch_desc(&tmBsh); tma_prefetch_desc(&tmB1);
+        if (POOL) tma_prefetch_desc(&tmPool);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < U_MAX_A; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
@@ -406,11 +411,15 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
     const int work_first = (int)(blockIdx.x >> 1), work_step = (int)(gridDim.x >> 1);
     const int Hc0 = (a.H + 1) >> 1, Hc1 = a.H >> 1, Wc0 = (a.W + 1) >> 1;
 
-    struct Tile { int py, ty, tx, img; bool live; };
-    auto decode = [&](int w) {
+    // iteration it of this pair = (region work_first + (it >> 1) * work_step, row parity it & 1): the two row-parity tiles of a
+    // region run back to back in ONE pair (the fused pool combines them; it also keeps the planes of the region in L2)
+    const int regions = a.work_total >> 1;
+    struct Tile { int py, ty, tx, img; bool live, done; };
+    auto decode = [&](int it) {
         Tile t;
-        t.py = w & 1;
-        const int q = w >> 1;
+        t.py = it & 1;
+        const int q = work_first + (it >> 1) * work_step;
+        t.done = q >= regions;
         const int r = fast_div(q, a.div_ntx);
         const int txq = q - r * a.ntx;
         const int aa = fast_div(r, a.div_ty);
@@ -418,7 +427,7 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
         t.tx = a.pair_img ? txq : 2 * txq + (int)cta_rank;
         t.img = a.pair_img ? 2 * aa + (int)cta_rank : aa;
         const int tx0 = a.pair_img ? txq : 2 * txq;
-        t.live = (t.ty * U_TH < (t.py ? Hc1 : Hc0)) && (tx0 * U_TW < Wc0);
+        t.live = !t.done && (t.ty * U_TH < (t.py ? Hc1 : Hc0)) && (tx0 * U_TW < Wc0);
         return t;
     };
     auto full_a_sig = [&](int s) { return mapa_shared(full_a(s), 0); };
@@ -433,11 +442,12 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
             auto load = [&](const CUtensorMap* map, uint32_t bytes, int c, int x, int y, int img) {
                 mbar_wait(empty_a(stage), phase ^ 1u);
                 if (leader) mbar_arrive_expect_tx(full_a(stage), 2 * bytes);
-                tma_load_4d_pair(a_base + (uint32_t)stage * U2_A_STAGE, map, full_a_sig(stage), c, x, y, img);
+                tma_load_4d_pair(a_base + (uint32_t)stage * A_STAGE, map, full_a_sig(stage), c, x, y, img);
                 if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
             };
-            for (int w = work_first; w < a.work_total; w += work_step) {
-                const Tile t = decode(w);
+            for (int it = 0;; ++it) {
+                const Tile t = decode(it);
+                if (t.done) break;
                 if (!t.live) continue;
                 const int x0 = t.tx * U_TW, y0 = t.ty * U_TH;
                 for (int ch = 0; ch < a.c0_chunks; ++ch)
@@ -466,8 +476,9 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                 tma_load_2d_pair(b_base + (uint32_t)slot * U2_B_SLOT, &tmB1, full_b_sig(slot), kb * 64, (int)cta_rank * 64);
                 if (++slot == a.b_slots) { slot = 0; phase ^= 1u; }
             };
-            for (int w = work_first; w < a.work_total; w += work_step) {
-                const Tile t = decode(w);
+            for (int it = 0;; ++it) {
+                const Tile t = decode(it);
+                if (t.done) break;
                 if (!t.live) continue;
                 for (int ch = 0; ch < a.c0_chunks; ++ch)
                     for (int plane = 0; plane < 4; ++plane) {
@@ -510,8 +521,9 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                 __syncwarp();
                 if (++sb == a.b_slots) { sb = 0; pb ^= 1u; }
             };
-            for (int w = work_first; w < a.work_total; w += work_step) {
-                const Tile t = decode(w);
+            for (int it = 0;; ++it) {
+                const Tile t = decode(it);
+                if (t.done) break;
                 if (!t.live) continue;
                 mbar_wait(tempty(acc), acc_phase ^ 1u);
                 tc_fence_after();
@@ -522,7 +534,7 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                     const int nky = ((plane >> 1) != t.py) ? 2 : 1;
                     mbar_wait(full_a(sa), pa);
                     tc_fence_after();
-                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * U2_A_STAGE, U_BW * 128);
+                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * A_STAGE, U_BW * 128);
                     for (int iy = 0; iy < nky; ++iy) {
                         // shared view: box column qx (both classes); single view: box column 1 - qx, class 1 - qx only
                         issue(d_tmem, da_stage + (uint64_t)((iy * U_BW + qx) * 8), idesc_sh, started, false, sa);
@@ -534,7 +546,7 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                 for (int ch = 0; ch < a.cl_chunks; ++ch) {
                     mbar_wait(full_a(sa), pa);
                     tc_fence_after();
-                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * U2_A_STAGE, U2_LOW_BW * 128);
+                    const uint64_t da_stage = make_sw128_desc(a_base + (uint32_t)sa * A_STAGE, U2_LOW_BW * 128);
                     for (int dy = 0; dy < 2; ++dy) {
                         issue(d_tmem, da_stage + (uint64_t)((dy * U2_LOW_BW + 1) * 8), idesc_sh, 1u, false, sa);
                         issue(d_tmem, da_stage + (uint64_t)((dy * U2_LOW_BW + 0) * 8), idesc_1, 1u, false, sa);
@@ -556,10 +568,12 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
         for (int c = et; c < CO; c += U_EPI_THREADS) { s_scale[c] = a.scale[c]; s_shift[c] = a.shift[c]; }
         named_bar_sync(1, U_EPI_THREADS);
         int acc = 0; uint32_t acc_phase = 0;
-        uint32_t store_groups = 0;
+        uint32_t store_groups = 0, pool_groups = 0;
+        uint32_t rmax[POOL ? CO / 2 : 1];                                // POOL: running 2x2 maximum of this plane pixel, bf16x2 per channel pair
         const uint32_t tempty_sig0 = mapa_shared(tempty(0), 0), tempty_sig1 = mapa_shared(tempty(1), 0);
-        for (int w = work_first; w < a.work_total; w += work_step) {
-            const Tile t = decode(w);
+        for (int it = 0;; ++it) {
+            const Tile t = decode(it);
+            if (t.done) break;
             if (!t.live) continue;
             const int Y = 2 * (t.ty * U_TH + ly) + t.py;
             uint32_t emask2[2] = {0u, 0u};
@@ -611,6 +625,15 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                 const uint32_t cbase = first_half ? 0u : 4u;
                 const uint32_t buf = store_groups & 1u;
                 const uint32_t o_stage = smem_base + stage_off + buf * U_OUT_STAGE;
+                if (POOL) {
+                    // the 2x2 pool window of plane pixel (y, x) is its four parity classes: columns c (px = 0) and CO + c (px = 1) of
+                    // the tiles py = 0 and py = 1.  Post-ReLU values: the first class initialises, the others take the maximum.
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t& m = rmax[POOL ? cc / 2 + i : 0];
+                        m = (t.py == 0 && px == 0) ? pk[i] : bf16x2_max(m, pk[i]);
+                    }
+                }
                 if (first_half) {
                     if (et == 0) bulk_wait_read<1>();
                     named_bar_sync(1, U_EPI_THREADS);
@@ -620,25 +643,50 @@ conv3x3_upm2_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant_
                 for (int i = 0; i < 4; ++i)
                     st_shared_v4(rbase + (((cbase + i) ^ ((uint32_t)row & 7u)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
                 if (!first_half) {
+                    const bool pool_now = POOL && t.py == 1 && px == 1;   // the last class of this 64-channel block: its maximum is final
+                    const uint32_t p_stage = smem_base + pool_off + (pool_groups & 1u) * U_OUT_STAGE;
+                    if (pool_now) {
+                        const uint32_t prow = p_stage + (uint32_t)row * 128u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int j = POOL ? (cc - 32) / 2 + 4 * i : 0;
+                            st_shared_v4(prow + (((uint32_t)i ^ ((uint32_t)row & 7u)) << 4), rmax[j], rmax[j + (POOL ? 1 : 0)], rmax[j + (POOL ? 2 : 0)],
+                                         rmax[j + (POOL ? 3 : 0)]);
+                        }
+                    }
                     fence_proxy_async();
                     named_bar_sync(1, U_EPI_THREADS);
                     if (et == 0) {
                         tma_store_4d(&maps.out[t.py * 2 + px], o_stage, cc - 32, t.tx * U_TW, t.ty * U_TH, t.img);
+                        if (pool_now) tma_store_4d(&tmPool, p_stage, cc - 32, t.tx * U_TW, t.ty * U_TH, t.img);
                         bulk_commit();
                     }
                     ++store_groups;
+                    if (pool_now) ++pool_groups;
                 }
             };
             uint32_t r0[32], r1[32];
             tmem_ld32(t_row, r0);
+            if (POOL) {
+#pragma unroll
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {               // unrolled: the running-maximum registers are indexed by column
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
+                    group(c0, true, r0);
+                    tmem_ld_wait();
+                    if (c0 + 64 < BLOCK_N) tmem_ld32(t_row + (uint32_t)(c0 + 64), r0);
+                    group(c0 + 32, false, r1);
+                }
+            } else {
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
-                tmem_ld_wait();
-                tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
-                group(c0, true, r0);
-                tmem_ld_wait();
-                if (c0 + 64 < BLOCK_N) tmem_ld32(t_row + (uint32_t)(c0 + 64), r0);
-                group(c0 + 32, false, r1);
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 64) {
+                    tmem_ld_wait();
+                    tmem_ld32(t_row + (uint32_t)(c0 + 32), r1);
+                    group(c0, true, r0);
+                    tmem_ld_wait();
+                    if (c0 + 64 < BLOCK_N) tmem_ld32(t_row + (uint32_t)(c0 + 64), r0);
+                    group(c0 + 32, false, r1);
+                }
             }
             tc_fence_before();
             __syncwarp();
@@ -805,16 +853,19 @@ static int launch_upm(const UpmMaps& maps, const CUtensorMap& mLow, const CUtens
     return ADN_OK;
 }
 
-static int launch_upm2(const UpmMaps& maps, const CUtensorMap& mLow, const CUtensorMap& mBsh, const CUtensorMap& mB1, Upm2Args& args,
-                       cudaStream_t stream) {
+template <bool POOL>
+static int launch_upm2(const UpmMaps& maps, const CUtensorMap& mLow, const CUtensorMap& mBsh, const CUtensorMap& mB1, const CUtensorMap& mPool,
+                       Upm2Args& args, cudaStream_t stream) {
     const int AUX = 2 * 128 * 4 + (2 * U_MAX_A + 2 * U_MAX_B + 4) * 8 + 16;
     constexpr int MAX_DYN = 232448;
-    const int budget = MAX_DYN - 1024 - AUX - 2 * U_OUT_STAGE;
-    args.a_stages = 4;
-    int sl = (budget - args.a_stages * U2_A_STAGE) / U2_B_SLOT;
+    const int staging = (POOL ? 4 : 2) * U_OUT_STAGE;
+    const int budget = MAX_DYN - 1024 - AUX - staging;
+    args.a_stage_bytes = args.cl_chunks > 0 ? U2_A_STAGE : U_A_STAGE;       // without a low tensor every box is a 17 x 9 skip plane
+    args.a_stages = POOL ? 3 : 4;
+    int sl = (budget - args.a_stages * args.a_stage_bytes) / U2_B_SLOT;
     args.b_slots = sl > U_MAX_B ? U_MAX_B : sl;
     if (args.b_slots < 4) return ADN_ERR_ARG;
-    const int smem = 1024 + args.a_stages * U2_A_STAGE + args.b_slots * U2_B_SLOT + 2 * U_OUT_STAGE + AUX;
+    const int smem = 1024 + args.a_stages * args.a_stage_bytes + args.b_slots * U2_B_SLOT + staging + AUX;
     const int max_pairs = num_sms() / 2;
     const int grid = 2 * (args.work_total < max_pairs ? args.work_total : max_pairs);
     cudaLaunchConfig_t cfg = {};
@@ -828,8 +879,8 @@ static int launch_upm2(const UpmMaps& maps, const CUtensorMap& mLow, const CUten
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     static unsigned char smem_set[64] = {0};
-    ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_upm2_kernel<128>, MAX_DYN, smem_set));
-    ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_upm2_kernel<128>, maps, mLow, mBsh, mB1, args));
+    ADN_CUDA_TRY(ensure_dyn_smem(conv3x3_upm2_kernel<128, POOL>, MAX_DYN, smem_set));
+    ADN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv3x3_upm2_kernel<128, POOL>, maps, mLow, mBsh, mB1, mPool, args));
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
@@ -852,9 +903,9 @@ extern "C" int adn_pack_upmerged_pair_weight_bf16(const void* w_merged, int c_ou
     return ADN_OK;
 }
 
-extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
-                                                      const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
-                                                      const float* wb, void* out, void* stream) {
+static int upm2_entry(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w, const void* bsh, const void* b1,
+                      int c_out, const float* scale, const float* shift_m, const float* wb, void* out, void* pool_out, void* stream) {
+    if (pool_out && (cl > 0 || !aligned16(pool_out))) return ADN_ERR_ARG;
     if (!skip || !bsh || !b1 || !scale || !shift_m || !out) return ADN_ERR_ARG;
     if (n <= 0 || h < 2 || w < 2 || c_out != 128) return ADN_ERR_ARG;
     if (c0 <= 0 || (c0 % 64) || cl < 0 || (cl % 64)) return ADN_ERR_ARG;
@@ -894,7 +945,26 @@ extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, 
     if (st != ADN_OK) return st;
     st = make_weight_map(&mB1, b1, c_out, 2 * (c0c * 8 + clc * 4) * 64, 64);
     if (st != ADN_OK) return st;
-    return launch_upm2(maps, mLow, mBsh, mB1, args, (cudaStream_t)stream);
+    args.pool = pool_out ? 1 : 0;
+    CUtensorMap mPool = mLow;
+    if (pool_out) {
+        st = make_act_map(&mPool, pool_out, n, h / 2, w / 2, c_out, U_TW, U_TH);
+        if (st != ADN_OK) return st;
+        return launch_upm2<true>(maps, mLow, mBsh, mB1, mPool, args, (cudaStream_t)stream);
+    }
+    return launch_upm2<false>(maps, mLow, mBsh, mB1, mPool, args, (cudaStream_t)stream);
+}
+
+extern "C" int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,
+                                                      const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
+                                                      const float* wb, void* out, void* stream) {
+    return upm2_entry(skip, c0, low, cl, hl, wl, n, h, w, bsh, b1, c_out, scale, shift_m, wb, out, nullptr, stream);
+}
+
+extern "C" int adn_conv3x3_pair_bn_relu_pool_bf16(const void* src, int c_in, int n, int h, int w, const void* bsh, const void* b1, int c_out,
+                                                  const float* scale, const float* shift, void* out, void* pool_out, void* stream) {
+    if (!pool_out || h < 2 || w < 2) return ADN_ERR_ARG;
+    return upm2_entry(src, c_in, nullptr, 0, 0, 0, n, h, w, bsh, b1, c_out, scale, shift, nullptr, out, pool_out, stream);
 }
 
 extern "C" int adn_conv3x3_upmerged_bn_relu_bf16(const void* skip, int c0, const void* low, int cl, int hl, int wl, int n, int h, int w,

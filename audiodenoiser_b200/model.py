@@ -229,10 +229,15 @@ class UNet(nn.Module):
             p = pk[layer]
             flops = 2.0 * n * hs[lvl] * wz[lvl] * p["co"] * 9 * (c0 + c1)
             # measured at batch 64 x (257,1034): upconv3.3 (128 -> 128) 0.89 -> 0.80 ms; downconv2.0 (64 -> 128, one chunk) 0.61 -> 0.62: not used
-            if self.plane128 and "bsh" in p and src1 is None and pool is None and c0 >= 128 and hs[lvl] >= 2 and wz[lvl] >= 2:
-                timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_upmerged_pair_bn_relu_bf16, src0.data_ptr(), c0, 0, 0, 0, 0, n, hs[lvl],
-                      wz[lvl], p["bsh"].data_ptr(), p["b1"].data_ptr(), 128, p["scale"].data_ptr(), p["shift"].data_ptr(), 0,
-                      dst.data_ptr(), s)
+            if self.plane128 and "bsh" in p and src1 is None and c0 >= 128 and hs[lvl] >= 2 and wz[lvl] >= 2:
+                if pool is None:
+                    timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_upmerged_pair_bn_relu_bf16, src0.data_ptr(), c0, 0, 0, 0, 0, n, hs[lvl],
+                          wz[lvl], p["bsh"].data_ptr(), p["b1"].data_ptr(), 128, p["scale"].data_ptr(), p["shift"].data_ptr(), 0,
+                          dst.data_ptr(), s)
+                else:                  # fused pool: running maximum over the four parity classes of a half-resolution pixel
+                    timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_pair_bn_relu_pool_bf16, src0.data_ptr(), c0, n, hs[lvl], wz[lvl],
+                          p["bsh"].data_ptr(), p["b1"].data_ptr(), 128, p["scale"].data_ptr(), p["shift"].data_ptr(), dst.data_ptr(),
+                          pool.data_ptr(), s)
                 return
             # the 2x2 max-pool of DownSampleLayer (model.py:31) is fused into the conv epilogue when `pool` is given
             timed(layer, "conv3x3", flops, 1, lib.adn_conv3x3_bn_relu_bf16, src0.data_ptr(), c0,

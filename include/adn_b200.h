@@ -197,6 +197,13 @@ int adn_conv3x3_upmerged_pair_bn_relu_bf16(const void* skip, int c0, const void*
                                            const void* bsh, const void* b1, int c_out, const float* scale, const float* shift_m,
                                            const float* wb, void* out_bf16, void* stream);
 
+/* Conv3x3 + BN + ReLU + fused MaxPool2d(2) (DownSampleLayer, model.py:29-32) for c_out == 128 in the same parity-class formulation:
+ * the 2x2 pool window of a half-resolution pixel is exactly its four parity classes, so the pooled value is the running maximum over
+ * the two column classes of a tile and the two row-parity tiles of a region (one CTA pair runs both back to back).  src (n,h,w,c_in),
+ * out (n,h,w,128), pool_out (n,h/2,w/2,128); bsh / b1 from adn_pack_upmerged_pair_weight_bf16(w_packed [128][9][c_in], cl = 0). */
+int adn_conv3x3_pair_bn_relu_pool_bf16(const void* src, int c_in, int n, int h, int w, const void* bsh, const void* b1, int c_out,
+                                       const float* scale, const float* shift, void* out_bf16, void* pool_out, void* stream);
+
 /* MaxPool2d(2) on NHWC bf16 (model.py:26,31), floor semantics: (n,h,w,c) -> (n,h/2,w/2,c). */
 int adn_maxpool2x2_bf16(const void* src, int n, int h, int w, int c, void* out, void* stream);
 

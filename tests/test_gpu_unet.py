@@ -277,6 +277,14 @@ def test_conv3x3_parity_class_kernel_without_low_tensor(n, c0, h, w):
     assert torch.isfinite(got).all()
     assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
     assert nrel(got, ref) <= 2.5e-3
+    # the fused-pool variant: same conv output bit for bit, pooled output = exact 2x2 floor pooling of the stored values
+    out2 = torch.full((n, h, w, co), float("nan"), dtype=torch.bfloat16, device=d)
+    pool = torch.full((n, h // 2, w // 2, co), float("nan"), dtype=torch.bfloat16, device=d)
+    _lib.check(lib.adn_conv3x3_pair_bn_relu_pool_bf16(a0.data_ptr(), c0, n, h, w, bsh.data_ptr(), b1.data_ptr(), co, sc.data_ptr(), sh.data_ptr(),
+                                                      out2.data_ptr(), pool.data_ptr(), s))
+    torch.cuda.synchronize()
+    assert torch.equal(out2.cpu(), out.cpu())
+    assert torch.equal(from_nhwc(pool.cpu()), F.max_pool2d(got, 2))
 
 
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 128, 64, 9, 7), (1, 1024, 512, 2, 3), (2, 256, 128, 16, 11), (1, 512, 256, 1, 1)])
