@@ -57,6 +57,9 @@ SIGNATURES = {
     "adn_spec_f16_crop_f32": (c_int, [P, c_int64, c_int, c_int, c_int, c_int, P, P]),
     "adn_spec_error_sums_f64": (c_int, [P, P, c_int64, P, P]),
     "adn_stats_pack_f64": (c_int, [P, c_int64, c_int64, P, P]),
+    "adn_zero_bytes": (c_int, [P, c_int64, P]),
+    "adn_copy_bytes": (c_int, [P, P, c_int64, P]),
+    "adn_i64_add_n": (c_int, [P, c_int, c_int64, P]),
     "adn_loss_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "adn_combined_loss_f32": (c_int, [P, P, c_int64, c_int, c_int, P, P, P, P]),
     # training step (train.py:65-72)

@@ -107,3 +107,36 @@ extern "C" int adn_istft_ola_host_f32(const float* mag_host, const float* phasor
     ADN_CUDA_TRY(cudaStreamSynchronize(s));
     return ADN_OK;
 }
+
+// cudaMemsetAsync behind the C ABI: the statistics vector of a step is zeroed by a memset node, not by a framework fill kernel
+extern "C" int adn_zero_bytes(void* dev, int64_t bytes, void* stream) {
+    if (!dev || bytes < 0) return ADN_ERR_ARG;
+    if (bytes == 0) return ADN_OK;
+    ADN_CUDA_TRY(cudaMemsetAsync(dev, 0, (size_t)bytes, (cudaStream_t)stream));
+    return ADN_OK;
+}
+
+// cudaMemcpyAsync (device to device) behind the C ABI: small bookkeeping copies of the training step as memcpy nodes
+extern "C" int adn_copy_bytes(void* dst_dev, const void* src_dev, int64_t bytes, void* stream) {
+    if (!dst_dev || !src_dev || bytes < 0) return ADN_ERR_ARG;
+    if (bytes == 0) return ADN_OK;
+    ADN_CUDA_TRY(cudaMemcpyAsync(dst_dev, src_dev, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return ADN_OK;
+}
+
+namespace adn {
+__global__ void i64_add_n_kernel(long long* v, int n, long long inc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += inc;
+}
+}  // namespace adn
+
+// v[0..n) += inc on the device (the num_batches_tracked counters of the 18 BatchNorm2d layers, one launch per training step)
+extern "C" int adn_i64_add_n(int64_t* v_dev, int n, int64_t inc, void* stream) {
+    if (!v_dev || n <= 0) return ADN_ERR_ARG;
+    int st = adn::check_device();
+    if (st != ADN_OK) return st;
+    adn::i64_add_n_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<long long*>(v_dev), n, (long long)inc);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}

@@ -206,7 +206,8 @@ class ShardedDenoiser:
             self._sums_work[self._sums_turn].wait()
             self._sums_work[self._sums_turn] = None
         self._sums = self._sums_bufs[self._sums_turn]
-        self._sums.zero_()
+        with torch.cuda.device(pred_mag.device):
+            _lib.check(_lib.load().adn_zero_bytes(self._sums.data_ptr(), 64, _lib.stream_ptr()), "adn_zero_bytes")
         p = pred_mag.float().contiguous(); t = target_mag.float().contiguous()
         if p.shape != t.shape:
             raise ValueError("pred and target must have the same shape")

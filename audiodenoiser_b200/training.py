@@ -82,7 +82,12 @@ class TrainEngine:
                 view.copy_(params[key].detach().to(dev, torch.float32))
                 params[key].data = view                      # the module's parameters now alias the flat buffer
         self.buffers = dict(self.model.named_buffers())
-        self._nbt = [b for k, b in self.buffers.items() if k.endswith("num_batches_tracked")]
+        # the num_batches_tracked counters alias ONE int64 vector (like the parameters alias the flat buffer): one launch advances all
+        nbt = [b for k, b in self.buffers.items() if k.endswith("num_batches_tracked")]
+        self._nbt_flat = torch.zeros(len(nbt), dtype=torch.int64, device=dev)
+        for i, b in enumerate(nbt):
+            self._nbt_flat[i] = b.to(dev)
+            b.data = self._nbt_flat[i]
         self.ones = torch.ones(1024, dtype=torch.float32, device=dev)
         self.zeros = torch.zeros(1024, dtype=torch.float32, device=dev)
         self.ws = torch.empty(int(self.lib.adn_train_workspace_bytes()), dtype=torch.uint8, device=dev)
@@ -278,7 +283,7 @@ class TrainEngine:
             _lib.check(lib.adn_head1x1_forward_f32(cur.data_ptr(), self._pptr("out.weight"), self._pptr("out.bias"), n * h * w, out.data_ptr(), s), "head")
             self.launch_count += 1
             sv["head_in"] = cur
-            torch._foreach_add_(self._nbt, 1)                # the 18 num_batches_tracked counters of nn.BatchNorm2d, one launch
+            _lib.check(lib.adn_i64_add_n(self._nbt_flat.data_ptr(), self._nbt_flat.numel(), 1, s), "nbt")      # the 18 num_batches_tracked counters
             self.launch_count += 1
         self.saved = sv
         return out
@@ -363,7 +368,7 @@ class TrainEngine:
             db = torch.empty(64, dtype=torch.float32, device=self.device)          # element 0 = d out.bias
             _lib.check(lib.adn_head1x1_backward(head_in.data_ptr(), d_out.data_ptr(), self._pptr("out.weight"), n * hs[0] * wz[0], dy.data_ptr(),
                                                 self._gptr("out.weight"), db.data_ptr(), wsp, s), "head bwd")
-            self.gview("out.bias").copy_(db[:1])
+            _lib.check(lib.adn_copy_bytes(self._gptr("out.bias"), db.data_ptr(), 4, s), "out.bias grad")
             self.launch_count += 5
             d_skip = {}
             cur_dy, cur_ld = dy, 64
@@ -430,11 +435,15 @@ class TrainEngine:
             _lib.check(lib.adn_combined_loss_backward_f32(pred.data_ptr(), target.data_ptr(), b, f, t, self.mel_fb.data_ptr(), 0.4, 0.4, 0.2,
                                                           self._loss_ws.data_ptr(), d_pred.data_ptr(), s), "loss bwd")
         self.launch_count += 6
-        return self.loss_out.clone(), d_pred
+        losses = torch.empty_like(self.loss_out)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.adn_copy_bytes(losses.data_ptr(), self.loss_out.data_ptr(), 16, s), "loss copy")
+        return losses, d_pred
 
     # ------------------------------------------------------------------ optimizer (train.py:66,70,71)
     def zero_grad(self):
-        self.G.zero_()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.adn_zero_bytes(self.G.data_ptr(), 4 * self.numel, _lib.stream_ptr()), "zero_grad")
 
     def _start_bucket(self, lo: int, hi: int):
         """DDP: start the asynchronous all-reduce(AVG) of G[lo:hi] (three buckets per step, launched from backward() in the order

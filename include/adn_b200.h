@@ -225,6 +225,12 @@ int adn_spec_error_sums_f64(const float* pred, const float* target, int64_t coun
  * adn_combined_loss_f32: total, stft, mel, l1 -- test.py:118-122) is given, sums8[4] = n_clips, sums8[5..7] = n_clips x the three terms,
  * so that the all-reduced vector yields exact full-batch means for unequal shards. */
 int adn_stats_pack_f64(double* sums8, int64_t numel, int64_t n_clips, const float* loss4, void* stream);
+/* Zero `bytes` bytes of device memory on `stream` (cudaMemsetAsync): how the caller zeroes the statistics vector above. */
+int adn_zero_bytes(void* dev, int64_t bytes, void* stream);
+/* Device-to-device cudaMemcpyAsync and v[0..n) += inc: the bookkeeping of a training step (loss vector, head-bias gradient, the 18
+ * num_batches_tracked counters of nn.BatchNorm2d) without framework kernels. */
+int adn_copy_bytes(void* dst_dev, const void* src_dev, int64_t bytes, void* stream);
+int adn_i64_add_n(int64_t* v_dev, int n, int64_t inc, void* stream);
 
 /* CombinedPerceptualLoss.forward (loss.py:83-95) = 0.4 * MultiScaleSTFTLoss (loss.py:12-35) + 0.4 * MelSpectrogramLoss
  * (loss.py:44-69) + 0.2 * L1Loss (loss.py:76,86) on (batch,1,freq,frames) float32 magnitude tensors (test.py:118-122,
