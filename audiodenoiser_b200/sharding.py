@@ -188,6 +188,7 @@ class ShardedDenoiser:
         self._sums_work = [None, None]
         self._peer = None                 # PeerGather (copy-engine all-gather), created on first use when available
         self._peer_failed = False
+        self.last_local = None
         self.gather_impl = "none"
 
     def local_range(self, n_total: int) -> tuple[int, int]:
@@ -225,6 +226,14 @@ class ShardedDenoiser:
         _lib.check(st, "adn_stats_pack_f64")
         return self._sums
 
+    def wait_sums(self):
+        """Make the CURRENT STREAM wait for the statistics all-reduce the latest ``step(..., overlap_gather=True)`` started (no host
+        synchronisation): after this the returned ``sums`` may be read on the stream, e.g. copied to the host."""
+        w = self._sums_work[self._sums_turn]
+        if w is not None:
+            w.wait()
+            self._sums_work[self._sums_turn] = None
+
     def finish(self):
         """Wait for the all-gathers started by ``step(..., overlap_gather=True)``."""
         if self._peer is not None:
@@ -259,6 +268,7 @@ class ShardedDenoiser:
                 sums = all_reduce_sums(sums, self.group)
         else:
             audio, sums = self.denoiser.denoise(wave_local), None
+        self.last_local = audio                     # this rank's own rows (valid on the compute stream now, whatever the gather does)
         if gather and self.world > 1 and overlap_gather and not self._peer_failed and audio.is_cuda and os.environ.get("ADN_GATHER", "peer") != "nccl":
             per = -(-n_total // self.world)
             if self._peer is None and PeerGather.available(audio.device):
