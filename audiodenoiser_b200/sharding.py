@@ -226,13 +226,17 @@ class ShardedDenoiser:
         _lib.check(st, "adn_stats_pack_f64")
         return self._sums
 
-    def wait_sums(self):
-        """Make the CURRENT STREAM wait for the statistics all-reduce the latest ``step(..., overlap_gather=True)`` started (no host
-        synchronisation): after this the returned ``sums`` may be read on the stream, e.g. copied to the host."""
-        w = self._sums_work[self._sums_turn]
+    def wait_sums(self, previous: bool = False):
+        """Make the CURRENT STREAM wait for the statistics all-reduce started by the latest ``step(..., overlap_gather=True)`` -- or,
+        with ``previous=True``, by the step before it -- and return that step's (now reduced) statistics vector; no host
+        synchronisation.  Reading every step's statistics one step late keeps the ranks decoupled: waiting for the CURRENT
+        step's all-reduce makes every rank's stream wait for the slowest rank in every step."""
+        turn = self._sums_turn ^ (1 if previous else 0)
+        w = self._sums_work[turn]
         if w is not None:
             w.wait()
-            self._sums_work[self._sums_turn] = None
+            self._sums_work[turn] = None
+        return self._sums_bufs[turn] if self._sums_bufs is not None else None
 
     def finish(self):
         """Wait for the all-gathers started by ``step(..., overlap_gather=True)``."""

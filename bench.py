@@ -313,11 +313,15 @@ def run_b200(args):
             # every rank reads ITS OWN rows and the group-reduced statistics back to the host; the all-gather of the audio runs on the
             # copy engines under the next step (as in the device-timed loop) and is completed inside the timed region by finish()
             _all, sums = job.step(wave_dev, n_total, clean_mags[(first + i) % rot], gather=True, overlap_gather=True)
-            job.wait_sums()
+            if world > 1 and i > 0:
+                sums = job.wait_sums(previous=True)      # N > 1: step i reads back the reduced statistics of step i - 1 (ranks stay decoupled)
             return job.last_local, sums
         stream_host_batches(fn, [host_batches[(first + i) % rot] for i in range(count)], [host_outs[i & 1] for i in range(count)],
                             [host_stats[i & 1] for i in range(count)], dev)
         job.finish()
+        if world > 1:                                    # ... and the last step's after the loop
+            host_stats[count & 1].copy_(job.wait_sums(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
 
     def timed(fn, steps, warmup, sampler):
         for i in range(warmup):
