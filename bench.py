@@ -666,7 +666,10 @@ def unet_conv_bytes(n, h, w):
         if l < 4:
             total += px[l + 1] * ch[l] * 2                              # fused max-pool output
     for l in (3, 2, 1, 0):
-        total += px[l] * (2 * ch[l] + ch[l]) * 2                        # conv over [skip, up]
+        if l > 0:
+            total += (px[l] * (ch[l] + ch[l]) + px[l + 1] * ch[l + 1]) * 2   # merged ConvTranspose + conv: skip and LOW tensor in, out
+        else:
+            total += px[l] * (2 * ch[l] + ch[l]) * 2                    # conv over [skip, up]
         total += px[l] * (ch[l] + (ch[l] if l else 0)) * 2              # second conv (level 0: fused head, fp32 out below)
     total += px[0] * 4
     return float(total)
