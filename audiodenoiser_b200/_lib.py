@@ -70,6 +70,7 @@ SIGNATURES = {
     "adn_pack_convt2x2_dgrad_weight_bf16": (c_int, [P, c_int, c_int, P, P]),
     "adn_pack_weights_table_bf16": (c_int, [P, c_int, P]),
     "adn_pack_weights_table_sel_bf16": (c_int, [P, c_int, c_int, P]),
+    "adn_pack_weights_table_flat_bf16": (c_int, [P, c_int, c_int, c_int, P]),
     "adn_bn_train_stats_f32": (c_int, [P, c_int64, c_int, P, P, c_float, c_float, P, P, P, P, P, P, P, P]),
     "adn_bn_relu_apply_bf16": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "adn_bn_relu_backward_bf16": (c_int, [P, c_int, P, c_int64, c_int, P, P, P, P, P, P, P, P, P]),

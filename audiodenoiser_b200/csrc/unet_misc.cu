@@ -63,16 +63,26 @@ struct PackEntry {
     int c_out, c_in, kind, pad;          // kind 0: Conv2d 3x3 (Co,Ci,3,3); 1: ConvTranspose2d 2x2 (Ci,Co,2,2)
 };
 __global__ void __launch_bounds__(256)
-pack_table_kernel(const PackEntry* __restrict__ table, int which) {      // which: bit 0 = forward packs, bit 1 = data-gradient packs
+pack_table_kernel(const PackEntry* __restrict__ table, int which, int n_flat) {      // which: bit 0 = forward packs, bit 1 = data-gradient packs
     __shared__ float tile[32][32 * 9 + 1];                        // [co][ci * 9 + tap], odd pitch: conflict-free both ways
-    const PackEntry e = table[blockIdx.y];
+    // n_flat > 0: ONE-dimensional grid, entry i owns the `pad` blocks after those of the entries before it (the host sized the grid
+    // to the sum).  The 2-D form launched 1 024 blocks per entry, of which the small layers use a handful: 21 504 block launches
+    // for 3 400 tiles cost more than the copies themselves.
+    int ent = blockIdx.y, bx = blockIdx.x, gx = gridDim.x;
+    if (n_flat > 0) {
+        int b = blockIdx.x;
+        ent = 0;
+        while (ent < n_flat - 1 && b >= table[ent].pad) { b -= table[ent].pad; ++ent; }
+        bx = b; gx = table[ent].pad;
+    }
+    const PackEntry e = table[ent];
     const int co_n = e.c_out, ci_n = e.c_in;
     if (e.kind == 0) {
         // 32 x 32 x 9 tiles through shared memory: the fp32 weights are read in 1 152-byte runs and both bf16 packs leave as
         // 64-byte runs (the destination-ordered version gathered 4-byte elements 36 B / Ci*36 B apart: 12-28 % sector use)
         const int ci_tiles = ci_n >> 5, tiles = (co_n >> 5) * ci_tiles;
         const int l = threadIdx.x & 31, grp = threadIdx.x >> 5;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        for (int t = bx; t < tiles; t += gx) {
             const int co0 = (t / ci_tiles) << 5, ci0 = (t % ci_tiles) << 5;
             for (int r = 0; r < 32; ++r) {
                 const float* src = e.w + ((long long)(co0 + r) * ci_n + ci0) * 9;
@@ -90,8 +100,8 @@ pack_table_kernel(const PackEntry* __restrict__ table, int which) {      // whic
             __syncthreads();
         }
     } else {
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        const long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const long long stride = (long long)gx * blockDim.x;
+        const long long i0 = bx * (long long)blockDim.x + threadIdx.x;
         const long long total = 4ll * co_n * ci_n;
         for (long long i = i0; i < total && (which & 1); i += stride) {          // fwd [q][co][ci]
             const int ci = (int)(i % ci_n);
@@ -352,7 +362,15 @@ extern "C" int adn_pack_convt2x2_dgrad_weight_bf16(const float* w, int c_in, int
 extern "C" int adn_pack_weights_table_sel_bf16(const void* table_dev, int n_entries, int which, void* stream) {
     if (!table_dev || n_entries <= 0 || n_entries > 65535 || which < 1 || which > 3) return ADN_ERR_ARG;
     int st = check_device(); if (st != ADN_OK) return st;
-    pack_table_kernel<<<dim3(1024, (unsigned)n_entries), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev), which);
+    pack_table_kernel<<<dim3(1024, (unsigned)n_entries), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev), which, 0);
+    ADN_LAUNCH_CHECK();
+    return ADN_OK;
+}
+
+extern "C" int adn_pack_weights_table_flat_bf16(const void* table_dev, int n_entries, int total_blocks, int which, void* stream) {
+    if (!table_dev || n_entries <= 0 || n_entries > 65535 || total_blocks <= 0 || which < 1 || which > 3) return ADN_ERR_ARG;
+    int st = check_device(); if (st != ADN_OK) return st;
+    pack_table_kernel<<<dim3((unsigned)total_blocks, 1), 256, 0, (cudaStream_t)stream>>>(static_cast<const PackEntry*>(table_dev), which, n_entries);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }

@@ -188,13 +188,14 @@ class TrainEngine:
             if cin == 1:
                 continue
             wf, wd = self.packed[(p, ci_)]
-            rows.append((self._pptr(f"{p}.double_conv.{ci_}.weight"), wf.data_ptr(), wd.data_ptr(), co, cin, 0, 0))
+            rows.append((self._pptr(f"{p}.double_conv.{ci_}.weight"), wf.data_ptr(), wd.data_ptr(), co, cin, 0, (co // 32) * (cin // 32)))
         for i, l in enumerate((3, 2, 1, 0)):
             ci, co = _CH[l + 1], _CH[l]
             wf, wd = self.packed[f"upconv{i + 1}.up"]
-            rows.append((self._pptr(f"upconv{i + 1}.up.weight"), wf.data_ptr(), wd.data_ptr(), co, ci, 1, 0))
+            rows.append((self._pptr(f"upconv{i + 1}.up.weight"), wf.data_ptr(), wd.data_ptr(), co, ci, 1, max(1, (4 * co * ci) // (256 * 16))))
         host = np.array(rows, dtype=rec)
         self._pack_n = len(rows)
+        self._pack_blocks = int(sum(r[6] for r in rows))          # `pad` = blocks per entry of the one-dimensional pack grid
         self._pack_table = torch.from_numpy(host.view(np.uint8).copy()).to(self.device)
 
     def repack(self, which: int = 3):
@@ -205,7 +206,8 @@ class TrainEngine:
         if self._pack_table is None:
             self._build_pack_table()
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.adn_pack_weights_table_sel_bf16(self._pack_table.data_ptr(), self._pack_n, which, _lib.stream_ptr()), "pack weights")
+            _lib.check(self.lib.adn_pack_weights_table_flat_bf16(self._pack_table.data_ptr(), self._pack_n, self._pack_blocks, which,
+                                                                 _lib.stream_ptr()), "pack weights")
         self.launch_count += 1
         if which & 1:
             self.model._packed = None          # the eval-mode forward of the module repacks from the updated parameters

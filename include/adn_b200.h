@@ -272,6 +272,9 @@ int adn_pack_weights_table_bf16(const void* table_dev, int n_entries, void* stre
 /* The same with a selection: which = 1 forward packs only, 2 data-gradient packs only, 3 both (the training step packs the forward
  * operands after AdamW and the data-gradient operands on a side stream under the next forward). */
 int adn_pack_weights_table_sel_bf16(const void* table_dev, int n_entries, int which, void* stream);
+/* The same over a ONE-dimensional grid: record field `pad` = the number of blocks entry i gets (kind 0: one block per 32 x 32 x 9 tile,
+ * (c_out/32)*(c_in/32); kind 1: any count >= 1), total_blocks = their sum.  The 2-D forms above launch 1 024 blocks per entry. */
+int adn_pack_weights_table_flat_bf16(const void* table_dev, int n_entries, int total_blocks, int which, void* stream);
 
 /* nn.BatchNorm2d in train() mode (model.py:12,15; eps 1e-5, momentum 0.1): batch statistics of z (pixels, c) NHWC bf16 ->
  * scale = gamma * invstd, shift = beta - mean * scale, mean, invstd; running_mean / running_var are updated in place

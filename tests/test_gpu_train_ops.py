@@ -330,3 +330,14 @@ def test_pack_table_equals_individual_packs():
     _lib.check(lib.adn_pack_weights_table_bf16(table.data_ptr(), len(rows), sp()))
     for (w, fwd, dg), (rf, rd) in zip(keep, refs):
         assert torch.equal(fwd, rf) and torch.equal(dg, rd)
+    # the one-dimensional grid (what the engine launches): `pad` = blocks per entry; and the forward / data-gradient selection
+    blocks = [(co // 32) * (ci // 32) if kind == 0 else 3 for kind, co, ci in shapes]
+    rows2 = [r[:6] + (b,) for r, b in zip(rows, blocks)]
+    table2 = torch.from_numpy(np.array(rows2, dtype=rec).view(np.uint8).copy()).to(d)
+    for which in (1, 2, 3):
+        for (w, fwd, dg) in keep:
+            fwd.zero_(); dg.zero_()
+        _lib.check(lib.adn_pack_weights_table_flat_bf16(table2.data_ptr(), len(rows2), sum(blocks), which, sp()))
+        for (w, fwd, dg), (rf, rd) in zip(keep, refs):
+            assert torch.equal(fwd, rf if which & 1 else torch.zeros_like(rf))
+            assert torch.equal(dg, rd if which & 2 else torch.zeros_like(rd))
