@@ -84,9 +84,25 @@ pack_table_kernel(const PackEntry* __restrict__ table, int which, int n_flat) { 
         const int l = threadIdx.x & 31, grp = threadIdx.x >> 5;
         for (int t = bx; t < tiles; t += gx) {
             const int co0 = (t / ci_tiles) << 5, ci0 = (t % ci_tiles) << 5;
-            for (int r = 0; r < 32; ++r) {
-                const float* src = e.w + ((long long)(co0 + r) * ci_n + ci0) * 9;
-                for (int i = threadIdx.x; i < 288; i += 256) tile[r][i] = src[i];
+            // 32 rows x 288 floats = 36 loads per thread, issued nine at a time before they are used (the row-by-row loop kept one or
+            // two loads in flight per thread and the kernel ran at a fifth of its memory floor)
+            const float* src0 = e.w + ((long long)co0 * ci_n + ci0) * 9;
+            const long long row_stride = (long long)ci_n * 9;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                float v[9];
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const int idx = (b * 9 + j) * 256 + threadIdx.x;          // < 9 216
+                    const int r = idx / 288, i = idx - r * 288;
+                    v[j] = src0[r * row_stride + i];
+                }
+#pragma unroll
+                for (int j = 0; j < 9; ++j) {
+                    const int idx = (b * 9 + j) * 256 + threadIdx.x;
+                    const int r = idx / 288, i = idx - r * 288;
+                    tile[r][i] = v[j];
+                }
             }
             __syncthreads();
             for (int it = grp; it < 288 && (which & 1); it += 8) {               // it = co_l * 9 + tap: 32 consecutive ci
