@@ -374,14 +374,28 @@ adamw_dev_step_kernel(float* __restrict__ p, const float* __restrict__ g, float*
     const float bc1 = 1.f - powf(beta1, t), bc2 = 1.f - powf(beta2, t);
     const float coef = clip ? clip[1] : 1.f;
     const float step = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
-        float pi = p[i] * (1.f - lr * weight_decay);
-        const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
-        const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
-        m[i] = mi; v[i] = vi;
+    auto upd = [&](float& pi, float gi, float& mi, float& vi) {        // one element, the arithmetic of adamw_kernel
+        gi *= coef;
+        pi *= (1.f - lr * weight_decay);
+        mi = fmaf(beta1, mi, (1.f - beta1) * gi);
+        vi = fmaf(beta2, vi, (1.f - beta2) * gi * gi);
         pi -= step * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
-        p[i] = pi;
+    };
+    // 16-byte accesses: four streams of 4-byte loads from 150 k threads keep ~2.4 MB in flight, half of what HBM needs (the flat
+    // buffers are 256-byte aligned)
+    const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                           reinterpret_cast<uintptr_t>(v)) & 15) == 0 ? n >> 2 : 0;
+    float4* p4 = reinterpret_cast<float4*>(p); const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m); float4* v4 = reinterpret_cast<float4*>(v);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+        upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+        m4[i] = mm; v4[i] = vv; p4[i] = pp;
+    }
+    for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        upd(pi, g[i], mi, vi);
+        m[i] = mi; v[i] = vi; p[i] = pi;
     }
 }
 
