@@ -318,7 +318,13 @@ head_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ w, lo
 __global__ void __launch_bounds__(TR_THREADS)
 sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ partial) {
     double s = 0.0;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long n4 = (reinterpret_cast<uintptr_t>(g) & 15) == 0 ? n >> 2 : 0;      // 16-byte loads (fixed order: still deterministic)
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = g4[i];
+        s += (double)v.x * (double)v.x + (double)v.y * (double)v.y + ((double)v.z * (double)v.z + (double)v.w * (double)v.w);
+    }
+    for (long long i = 4 * n4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = g[i];
         s += (double)v * (double)v;
     }
