@@ -93,7 +93,10 @@ loss_spectral_kernel(const float* __restrict__ env, int T, const float* __restri
 
     // ---- loss.py:22-35: rectangular-window magnitudes at three scales
     const int nffts[3] = {63, 32, 16}, hops[3] = {16, 8, 4};
+    // blockIdx.y selects ONE of the four transforms (three rectangular scales, mel): 4 x batch CTAs instead of batch (64 CTAs on 148
+    // SMs each running the four transforms back to back took 110 us per step at the benchmark shape)
     for (int s = 0; s < 3; ++s) {
+        if ((int)blockIdx.y != s) continue;
         const int n = nffts[s], hop = hops[s], pad = n / 2, bins = n / 2 + 1;
         const int frames = 1 + (T + 2 * pad - n) / hop;
         __syncthreads();
@@ -122,7 +125,7 @@ loss_spectral_kernel(const float* __restrict__ env, int T, const float* __restri
     }
 
     // ---- loss.py:40-69: mel power spectrogram (Hann 63, reflect padding), 8 frames per pass
-    {
+    if (blockIdx.y == 3) {
         const int pad = MEL_NFFT / 2;
         const int frames = 1 + (T + 2 * pad - MEL_NFFT) / MEL_HOP;
         __syncthreads();
@@ -170,13 +173,22 @@ loss_spectral_kernel(const float* __restrict__ env, int T, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
-__global__ void loss_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ l1_partial, int n_l1, int B, int F,
-                                     int T, float* __restrict__ out4) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double s[4] = {0, 0, 0, 0}, l1 = 0.0;
-    for (int b = 0; b < B; ++b)
-        for (int j = 0; j < 4; ++j) s[j] += sums[(size_t)b * 4 + j];
-    for (int i = 0; i < n_l1; ++i) l1 += l1_partial[i];
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const double* __restrict__ sums, const double* __restrict__ l1_partial, int n_l1, int B, int F,
+                     int T, float* __restrict__ out4) {
+    // 256 threads, strided partial sums folded in a fixed order (deterministic); one thread walking the B x 4 + n_l1 partials took 90 us
+    __shared__ double red[8];
+    __shared__ double tot[5];
+    for (int j = 0; j < 5; ++j) {
+        double a = 0.0;
+        if (j < 4) { for (int b = threadIdx.x; b < B; b += blockDim.x) a += sums[(size_t)b * 4 + j]; }
+        else { for (int i = threadIdx.x; i < n_l1; i += blockDim.x) a += l1_partial[i]; }
+        const double t = block_sum(a, red);
+        if (threadIdx.x == 0) tot[j] = t;
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double s[4] = {tot[0], tot[1], tot[2], tot[3]}, l1 = tot[4];
     const int nffts[3] = {63, 32, 16}, hops[3] = {16, 8, 4};
     double stft = 0.0;
     for (int j = 0; j < 3; ++j) {
@@ -396,9 +408,9 @@ extern "C" int adn_combined_loss_f32(const float* pred, const float* target, int
     const size_t smem = (size_t)(2 * frames + 3 * 64 + MEL_BINS * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float);
     static unsigned char smem_set[64] = {0};
     ADN_CUDA_TRY(ensure_dyn_smem(loss_spectral_kernel, (int)((2 * LOSS_MAX_T + 3 * 64 + MEL_BINS * MEL_N + 2 * 8 * MEL_BINS) * sizeof(float)), smem_set));
-    loss_spectral_kernel<<<(unsigned)batch, 256, smem, s>>>(env, frames, mel_fb_32x64, sums);
+    loss_spectral_kernel<<<dim3((unsigned)batch, 4), 256, smem, s>>>(env, frames, mel_fb_32x64, sums);
     ADN_LAUNCH_CHECK();
-    loss_finalize_kernel<<<1, 32, 0, s>>>(sums, l1p, (int)(batch * tx), (int)batch, freq, frames, out4);
+    loss_finalize_kernel<<<1, 256, 0, s>>>(sums, l1p, (int)(batch * tx), (int)batch, freq, frames, out4);
     ADN_LAUNCH_CHECK();
     return ADN_OK;
 }
