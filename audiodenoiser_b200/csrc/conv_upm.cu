@@ -340,6 +340,12 @@ conv3x3_upm_kernel(const __grid_constant__ UpmMaps maps, const __grid_constant__
 //   * the planes are loaded once for two classes, so the TMA writes per UMMA cycle drop from 66 to 48 B/clk and the mean
 //     operand read from 96 to 75 B/clk.
 // B comes from two packed tensors: Bsh [2*CO][..] (shared views) and B1 [CO][..] (single views), blocks in consumption order.
+// Measured at batch 64 x (257,1034): upconv3 (ConvTranspose 256 -> 128 + conv over 128 + 128 channels) 0.38 + 1.69 -> 1.50-1.53 ms.
+// Without a low tensor (cl_chunks = 0) the kernel is a plain Conv3x3 + BN + ReLU with 128 output channels in the same formulation
+// (upconv3.3: 0.89 -> 0.80 ms against conv_halo's CTA-pair kernel).  POOL adds the fused MaxPool2d(2) of DownSampleLayer
+// (model.py:31): the pool window of a half-resolution pixel is exactly its four parity classes, so every epilogue thread keeps a
+// running bf16x2 maximum over the two column classes of a tile and over the two row-parity tiles of a region -- a CTA pair walks its
+// regions with py = 0, 1 back to back -- and stores the pooled tile after the second one (downconv2.3: 1.01 -> 0.94 ms).
 constexpr int U2_LOW_BW = U_TW + 2;                               // the low tile spans columns x0-1 .. x0+8 for the two classes
 constexpr int U2_A_STAGE = ((U_BH * U2_LOW_BW * 128) + 1023) & ~1023;   // 22 528 B (skip plane boxes are 17 x 9)
 constexpr int U2_B_SLOT = 128 * 128;                              // one CTA's half of a shared block (a single block uses half of it)
